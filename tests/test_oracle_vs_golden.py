@@ -1,0 +1,83 @@
+"""Pins the CPU oracle (oracle/farneback_oracle.c) against golden vectors produced by the
+reference's own dependency, cv2 (tests/golden/make_golden.py).  CPU only.
+
+The oracle is far inside the north_star tolerance (mean 1e-3 / max 1e-2 px); the gate here is
+two orders tighter so that the oracle can serve as the per-stage checker for the CUDA kernels.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden, epe, GOLDEN_DIR
+
+ORACLE_MEAN_TOL = 1e-5
+ORACLE_MAX_TOL = 2e-4
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_farneback_flow_matches_cv2_golden(oracle, name):
+    g = load_golden(name)
+    init = g.get("init_flow")
+    flow = oracle.farneback(g["prev"], g["next"], None if init is None else init.copy(), **g["kw"])
+    assert flow.shape == g["flow"].shape and flow.dtype == np.float32
+    mean, mx = epe(flow, g["flow"])
+    assert mean <= ORACLE_MEAN_TOL and mx <= ORACLE_MAX_TOL, (name, mean, mx)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_viz_on_cv2_flow_is_bit_exact_in_hue_and_value(oracle, name):
+    g = load_golden(name)
+    bgr, hue, val = oracle.viz(g["flow"], 0, return_hv=True)
+    assert np.array_equal(hue, g["hue"])
+    assert np.array_equal(val, g["val"])
+    d = np.abs(bgr.astype(np.int16) - g["bgr"].astype(np.int16))
+    assert d.max() <= 1                     # cv2's body truncates, its tail rounds
+    assert (d == 0).all(-1).mean() > 0.85
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_summed_magnitude(oracle, name):
+    g = load_golden(name)
+    s = oracle.sum_magnitude(g["flow"])
+    assert abs(s - float(g["magsum"])) <= 1e-6 * abs(float(g["magsum"]))
+
+
+def test_cart_to_polar_matches_golden_hue_path(oracle):
+    g = load_golden("ref_320x180")
+    mag, ang = oracle.cart_to_polar(g["flow"])
+    hue = ((ang * np.float32(180)) / np.float32(np.pi)).astype(np.int64) & 255
+    assert np.array_equal(hue.astype(np.uint8), g["hue"])
+    assert mag.min() >= 0 and ang.min() >= 0 and ang.max() < 2 * np.pi + 1e-5
+
+
+def test_hsv2bgr_table_body_and_tail(oracle):
+    z = np.load(GOLDEN_DIR + "/hsv2bgr_table.npz")
+    assert np.array_equal(oracle.hsv_table(0), z["body"])    # truncating form == cv2's vector body, 65536/65536
+    assert np.array_equal(oracle.hsv_table(1), z["tail"])    # rounding form   == cv2's scalar tail, 65536/65536
+
+
+def test_scale_schedule_matches_survey_probes(oracle):
+    s = oracle.scale_schedule(1920, 1080, 0.5, 3)
+    assert [(w, h, k) for _, w, h, k, _, _ in s] == [(240, 135, 19), (480, 270, 9), (960, 540, 3), (1920, 1080, 3)]
+    s = oracle.scale_schedule(3840, 2160, 0.5, 5)
+    assert [(w, h, k) for _, w, h, k, _, _ in s] == [(120, 68, 79), (240, 135, 39), (480, 270, 19), (960, 540, 9),
+                                                    (1920, 1080, 3), (3840, 2160, 3)]
+    s = oracle.scale_schedule(129, 77, 0.5, 3)
+    assert [(w, h) for _, w, h, _, _, _ in s] == [(64, 38), (129, 77)]
+    assert len(oracle.scale_schedule(40, 40, 0.5, 3)) == 1
+
+
+def test_degenerate_parameters_are_finite(oracle):
+    g = load_golden("levels0_64x48")
+    for kw in (dict(iterations=0), dict(winsize=1), dict(poly_n=1), dict(levels=-2)):
+        p = dict(g["kw"]); p.update(kw)
+        f = oracle.farneback(g["prev"], g["next"], None, **p)
+        assert np.isfinite(f).all()
+    p = dict(g["kw"]); p["iterations"] = 0
+    assert not oracle.farneback(g["prev"], g["next"], None, **p).any()
+
+
+def test_oracle_rejects_pyr_scale_ge_1(oracle):
+    g = load_golden("levels0_64x48")
+    p = dict(g["kw"]); p["pyr_scale"] = 1.0
+    with pytest.raises(ValueError):
+        oracle.farneback(g["prev"], g["next"], None, **p)
