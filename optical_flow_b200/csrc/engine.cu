@@ -1,0 +1,910 @@
+// engine.cu -- context, workspaces, the per-scale schedule of cv2.calcOpticalFlowFarneback
+//  and the C ABI declared in include/optflow_b200.h.
+//
+// Host logic mirrored from the reference's dependency (FarnebackOpticalFlowImpl::calc):
+//   K = number of extra scales (coarsest >= 32 px); for k = K..0:
+//     flow_k   = zeros | area-resized initial flow * scale | bilinear up-sample of flow_{k+1} * 1/pyr_scale
+//     R[i]     = polyexp(level_image(frame_i, k))           i = 0, 1
+//     M        = UpdateMatrices(R0, R1, flow_k)
+//     repeat iterations:  flow_k = solve(blur(M));  M = UpdateMatrices(...) unless last
+// The per-frame part (level images + polynomial expansion, every scale) is kept in one of two
+// "frame slots", so that inside a shot each frame is expanded once and used by both of its pairs.
+#include "common.cuh"
+#include "launch.cuh"
+#include "../../include/optflow_b200.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ofb;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct Level {
+    int k = 0, W = 0, H = 0, pitch = 0, ksize = 0;
+    double sigma = 0, scale = 1;
+    float* taps = nullptr;          // device, ksize floats
+    float* R[2] = {nullptr, nullptr};   // 5 planes each, per frame slot
+    float2* flow = nullptr;         // tight (H, W) float2; null at k == 0 (caller's buffer is used)
+    size_t plane() const { return (size_t)H * pitch; }
+};
+
+struct Plan {
+    bool valid = false;
+    int W = 0, H = 0, dtype = 0;
+    ofb_params p{};
+    std::vector<Level> lv;          // index = k (0 = full resolution)
+    int K = 0;
+    // scratch sized for scale 0
+    float* T = nullptr;             // H x pitch0   (horizontal pyramid pass)
+    float* I = nullptr;             // H0 x pitch0  (level image)
+    float* tmp3 = nullptr;          // 3 planes     (generic polyexp)
+    float* M = nullptr;             // 5 planes
+    double* btmp = nullptr;         // 5 planes f64 (generic blur; reused as f32 by the Gaussian path)
+    float* poly = nullptr;          // g, xg, xxg : 3 * (2n+1)
+    float* gtaps = nullptr;         // half taps of the Gaussian window, m+1
+    PolyConst pc{};
+    void* frame[2] = {nullptr, nullptr};    // device copies of the two frames (tight rows)
+    float2* flow0 = nullptr;        // scale-0 flow when the caller keeps it on the device side of the host API
+    float2* flow0b = nullptr;       // second one for shots that download the flow
+    uint8_t* bgr[2] = {nullptr, nullptr};
+    std::vector<void*> allocs;
+};
+
+}  // namespace
+
+struct ofb_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2]{}, ev_frame_free[2]{}, ev_out_ready[2]{}, ev_out_free[2]{}, ev_t0 = nullptr, ev_t1 = nullptr;
+    std::string err;
+    Profiler prof;
+    bool generic = false;
+    Plan plan;
+    unsigned* minmax = nullptr;     // [2]
+    double* sumacc = nullptr;       // [1]
+    float* sumout = nullptr;        // [1] device staging of one magnitude sum
+    float* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // scratch for stage / companion entry points
+    size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(ofb_context* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, OFB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+// ---- A.1 ------------------------------------------------------------------------------------
+int num_scales(int W, int H, double pyr_scale, int levels)
+{
+    int k; double scale = 1.0;
+    for (k = 0; k < levels; k++) {
+        scale *= pyr_scale;
+        if (W * scale < 32 || H * scale < 32) break;
+    }
+    return k;
+}
+
+void scale_geometry(int W, int H, double pyr_scale, int k, int* Wk, int* Hk, int* ksize, double* sigma, double* scale_out)
+{
+    double scale = 1.0;
+    for (int i = 0; i < k; i++) scale *= pyr_scale;
+    double s = (1.0 / scale - 1.0) * 0.5;
+    int sz = (int)lrint(s * 5.0) | 1;
+    if (sz < 3) sz = 3;
+    *Wk = (int)lrint(W * scale);
+    *Hk = (int)lrint(H * scale);
+    *ksize = sz; *sigma = s;
+    if (scale_out) *scale_out = scale;
+}
+
+// cv::getGaussianKernel(n, sigma, CV_32F)
+void gaussian_taps(int n, double sigma, std::vector<float>& out)
+{
+    out.resize(n);
+    if (sigma <= 0 && n <= 7 && (n & 1)) {
+        static const float k1[] = {1.f}, k3[] = {0.25f, 0.5f, 0.25f}, k5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f},
+                           k7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+        const float* f = n == 1 ? k1 : n == 3 ? k3 : n == 5 ? k5 : k7;
+        for (int i = 0; i < n; i++) out[i] = f[i];
+        return;
+    }
+    double sg = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+    double scale2 = -0.5 / (sg * sg), sum = 0;
+    std::vector<double> t(n);
+    for (int i = 0; i < n; i++) { double x = i - (n - 1) * 0.5; t[i] = std::exp(scale2 * x * x); sum += t[i]; }
+    sum = 1.0 / sum;
+    for (int i = 0; i < n; i++) out[i] = (float)(t[i] * sum);
+}
+
+// A.5: FarnebackPrepareGaussian
+void poly_constants(int n, double sigma, std::vector<float>& tab, double ig[4])
+{
+    int len = 2 * n + 1;
+    tab.assign(3 * len, 0.f);
+    float* g = tab.data() + n; float* xg = g + len; float* xxg = xg + len;
+    if (sigma < FLT_EPSILON) sigma = n * 0.3;
+    double s = 0.;
+    for (int x = -n; x <= n; x++) { g[x] = (float)std::exp(-x * x / (2 * sigma * sigma)); s += g[x]; }
+    s = 1. / s;
+    for (int x = -n; x <= n; x++) {
+        g[x] = (float)(g[x] * s);
+        xg[x] = (float)(x * g[x]);
+        xxg[x] = (float)(x * x * g[x]);
+    }
+    double G00 = 0, G11 = 0, G33 = 0, G55 = 0;
+    for (int y = -n; y <= n; y++)
+        for (int x = -n; x <= n; x++) {
+            float gg = g[y] * g[x];
+            G00 += gg; G11 += gg * x * x; G33 += gg * x * x * x * x; G55 += gg * x * x * y * y;
+        }
+    double a = G00, b = G11, c = G33, d = G55, den = a * (c + d) - 2 * b * b;
+    ig[0] = 1.0 / G11; ig[1] = -b / den; ig[2] = (a * c - b * b) / ((c - d) * den); ig[3] = 1.0 / G55;
+}
+
+void gauss_half_taps(int winsize, std::vector<float>& k)
+{
+    int m = winsize / 2;
+    k.resize(m + 1);
+    double sigma = m * 0.3, s = 1;
+    k[0] = (float)s;
+    for (int i = 1; i <= m; i++) { float t = (float)std::exp(-i * i / (2 * sigma * sigma)); k[i] = t; s += t * 2; }
+    s = 1. / s;
+    for (int i = 0; i <= m; i++) k[i] = (float)(k[i] * s);
+}
+
+// ---- plan -----------------------------------------------------------------------------------
+void free_plan(Plan& pl)
+{
+    for (void* p : pl.allocs) cudaFree(p);
+    pl = Plan();
+}
+
+template <class T> int dalloc(ofb_context* ctx, Plan& pl, T** out, size_t count)
+{
+    void* p = nullptr;
+    CU(cudaMalloc(&p, count * sizeof(T) + 256));
+    pl.allocs.push_back(p);
+    *out = (T*)p;
+    return 0;
+}
+
+bool same_params(const ofb_params& a, const ofb_params& b)
+{
+    return a.pyr_scale == b.pyr_scale && a.levels == b.levels && a.winsize == b.winsize && a.iterations == b.iterations &&
+           a.poly_n == b.poly_n && a.poly_sigma == b.poly_sigma && a.flags == b.flags;
+}
+
+int validate(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p)
+{
+    if (!ctx) return fail(nullptr, OFB_ERR_BAD_ARG, "null context");
+    if (!p) return fail(ctx, OFB_ERR_BAD_ARG, "null params");
+    if (dtype != OFB_U8 && dtype != OFB_F32) return fail(ctx, OFB_ERR_BAD_ARG, "dtype must be OFB_U8 or OFB_F32");
+    if (W <= 0 || H <= 0 || !(p->pyr_scale < 1))
+        return fail(ctx, OFB_ERR_ASSERT,
+                    "prev0.size() == next0.size() && prev0.channels() == next0.channels() && prev0.channels() == 1 && pyrScale_ < 1");
+    if (!(p->pyr_scale > 0)) return fail(ctx, OFB_ERR_UNSUPPORTED, "pyr_scale must be > 0");
+    if (p->poly_n < 1 || p->poly_n > 64) return fail(ctx, OFB_ERR_UNSUPPORTED, "poly_n outside 1..64");
+    if (p->winsize < 1 || p->winsize > 1024) return fail(ctx, OFB_ERR_UNSUPPORTED, "winsize outside 1..1024");
+    if (p->iterations < 0) return fail(ctx, OFB_ERR_UNSUPPORTED, "iterations < 0");
+    return 0;
+}
+
+int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p)
+{
+    Plan& pl = ctx->plan;
+    if (pl.valid && pl.W == W && pl.H == H && pl.dtype == dtype && same_params(pl.p, *p)) return 0;
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_h2d));
+    CU(cudaStreamSynchronize(ctx->s_d2h));
+    free_plan(pl);
+    pl.W = W; pl.H = H; pl.dtype = dtype; pl.p = *p;
+    pl.K = num_scales(W, H, p->pyr_scale, p->levels);
+    pl.lv.resize(pl.K + 1);
+    for (int k = 0; k <= pl.K; k++) {
+        Level& l = pl.lv[k];
+        l.k = k;
+        scale_geometry(W, H, p->pyr_scale, k, &l.W, &l.H, &l.ksize, &l.sigma, &l.scale);
+        if (l.W < 1 || l.H < 1) return fail(ctx, OFB_ERR_UNSUPPORTED, "a pyramid level collapsed to zero size");
+        l.pitch = round_up(l.W, 32);
+        std::vector<float> taps;
+        gaussian_taps(l.ksize, l.sigma, taps);
+        if (int rc = dalloc(ctx, pl, &l.taps, taps.size())) return rc;
+        CU(cudaMemcpy(l.taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        for (int s = 0; s < 2; s++)
+            if (int rc = dalloc(ctx, pl, &l.R[s], 5 * l.plane())) return rc;
+        if (k > 0)
+            if (int rc = dalloc(ctx, pl, &l.flow, (size_t)l.W * l.H)) return rc;
+    }
+    const Level& l0 = pl.lv[0];
+    size_t plane0 = l0.plane();
+    if (int rc = dalloc(ctx, pl, &pl.T, (size_t)H * l0.pitch)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.I, plane0)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.tmp3, 3 * plane0)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.M, 5 * plane0)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.btmp, 5 * plane0)) return rc;
+    std::vector<float> tab; double ig[4];
+    poly_constants(p->poly_n, p->poly_sigma, tab, ig);
+    if (int rc = dalloc(ctx, pl, &pl.poly, tab.size())) return rc;
+    CU(cudaMemcpy(pl.poly, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    int len = 2 * p->poly_n + 1;
+    pl.pc = PolyConst{pl.poly, pl.poly + len, pl.poly + 2 * len, p->poly_n, ig[0], ig[1], ig[2], ig[3]};
+    std::vector<float> gk;
+    gauss_half_taps(p->winsize, gk);
+    if (int rc = dalloc(ctx, pl, &pl.gtaps, gk.size())) return rc;
+    CU(cudaMemcpy(pl.gtaps, gk.data(), gk.size() * sizeof(float), cudaMemcpyHostToDevice));
+    size_t esz = dtype == OFB_U8 ? 1 : 4;
+    for (int s = 0; s < 2; s++) {
+        uint8_t* f = nullptr;
+        if (int rc = dalloc(ctx, pl, &f, (size_t)W * H * esz)) return rc;
+        pl.frame[s] = f;
+        if (int rc = dalloc(ctx, pl, &pl.bgr[s], (size_t)W * H * 3)) return rc;
+    }
+    if (int rc = dalloc(ctx, pl, &pl.flow0, (size_t)W * H)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.flow0b, (size_t)W * H)) return rc;
+    pl.valid = true;
+    return 0;
+}
+
+Planes5 planes(float* base, const Level& l) { return Planes5{base, l.plane(), l.pitch}; }
+
+// Per-frame part: level images + polynomial expansion for every scale, into frame slot `slot`.
+void expand_frame(ofb_context* ctx, Launch& L, const void* d_frame, size_t pitch_bytes, int slot)
+{
+    Plan& pl = ctx->plan;
+    for (int k = pl.K; k >= 0; k--) {
+        Level& l = pl.lv[k];
+        launch_pyr_h(L, d_frame, pl.dtype, pl.W, pl.H, pitch_bytes, l.taps, l.ksize, pl.T, l.W, l.pitch);
+        launch_pyr_v(L, pl.T, pl.H, l.pitch, l.taps, l.ksize, pl.I, l.W, l.H, l.pitch);
+        launch_polyexp(L, pl.I, l.W, l.H, l.pitch, pl.pc, pl.tmp3, planes(l.R[slot], l), ctx->generic);
+    }
+}
+
+// Per-pair part: coarse-to-fine iterations; d_flow is the (H, W) float2 output (read first when
+// OPTFLOW_USE_INITIAL_FLOW).
+void solve_pair(ofb_context* ctx, Launch& L, int slot0, int slot1, float2* d_flow)
+{
+    Plan& pl = ctx->plan;
+    const ofb_params& p = pl.p;
+    const bool gaussian = (p.flags & OFB_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
+    for (int k = pl.K; k >= 0; k--) {
+        Level& l = pl.lv[k];
+        float2* flow = k == 0 ? d_flow : l.flow;
+        if (k == pl.K) {
+            if (p.flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
+                if (k > 0) launch_area_flow(L, d_flow, pl.W, pl.H, flow, l.W, l.H, (float)l.scale);
+                // k == 0: same-size INTER_AREA is a copy and scale == 1: the buffer already holds it
+            } else {
+                cudaMemsetAsync(flow, 0, sizeof(float2) * (size_t)l.W * l.H, L.stream);
+            }
+        } else {
+            const Level& c = pl.lv[k + 1];
+            launch_upsample_flow(L, c.flow, c.W, c.H, flow, l.W, l.H, (float)(1. / p.pyr_scale));
+        }
+        Planes5 R0 = planes(l.R[slot0], l), R1 = planes(l.R[slot1], l), M = planes(pl.M, l);
+        launch_update_matrices(L, R0, R1, flow, l.W, l.H, M);
+        for (int i = 0; i < p.iterations; i++) {
+            if (gaussian)
+                launch_blur_solve_gauss(L, M, l.W, l.H, p.winsize, pl.gtaps, (float*)pl.btmp, flow, ctx->generic);
+            else
+                launch_blur_solve_box(L, M, l.W, l.H, p.winsize, pl.btmp, flow, ctx->generic);
+            if (i < p.iterations - 1) launch_update_matrices(L, R0, R1, flow, l.W, l.H, M);
+        }
+    }
+}
+
+void picture(ofb_context* ctx, Launch& L, const float2* d_flow, size_t n, uint8_t* d_bgr)
+{
+    launch_minmax_reset(L, ctx->minmax);
+    launch_minmax_mag(L, d_flow, n, ctx->minmax);
+    launch_flow_to_bgr(L, d_flow, n, ctx->minmax, d_bgr);
+}
+
+int stage_buf(ofb_context* ctx, int i, size_t bytes, float** out)
+{
+    if (ctx->stage_bytes[i] < bytes) {
+        if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        ctx->stage[i] = nullptr; ctx->stage_bytes[i] = 0;
+        CU(cudaMalloc((void**)&ctx->stage[i], bytes + 256));
+        ctx->stage_bytes[i] = bytes;
+    }
+    *out = ctx->stage[i];
+    return 0;
+}
+
+int upload_frame(ofb_context* ctx, const void* src, size_t pitch, int W, int H, int dtype, void* dst, cudaStream_t s)
+{
+    size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4);
+    if (pitch == 0) pitch = row;
+    if (pitch < row) return fail(ctx, OFB_ERR_BAD_ARG, "row pitch smaller than a row");
+    CU(cudaMemcpy2DAsync(dst, row, src, pitch, row, H, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+#pragma GCC visibility push(default)
+
+int ofb_abi_version(void) { return OFB_ABI_VERSION; }
+const char* ofb_global_error(void) { return g_error.c_str(); }
+
+int ofb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ofb_create(int device, ofb_context** out)
+{
+    ofb_context* ctx = nullptr;
+    if (!out) return fail(nullptr, OFB_ERR_BAD_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, OFB_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, OFB_ERR_BAD_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, OFB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; kernels are built for sm_100a only");
+    ofb_context* c = new ofb_context();
+    ctx = c;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    set_sm_count(c->sm_count);
+    cudaError_t rc = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (rc == cudaSuccess) rc = r; };
+    ok(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        ok(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&c->ev_frame_free[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&c->ev_out_ready[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&c->ev_out_free[i], cudaEventDisableTiming));
+    }
+    ok(cudaEventCreate(&c->ev_t0));
+    ok(cudaEventCreate(&c->ev_t1));
+    ok(cudaMalloc((void**)&c->minmax, 256));
+    ok(cudaMalloc((void**)&c->sumacc, 256));
+    ok(cudaMalloc((void**)&c->sumout, 256));
+    if (rc != cudaSuccess) {
+        std::string m = std::string("context setup: ") + cudaGetErrorString(rc);
+        delete c;
+        return fail(nullptr, OFB_ERR_CUDA, m);
+    }
+    *out = c;
+    return OFB_OK;
+}
+
+void ofb_destroy(ofb_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->prof.collect();
+    free_plan(ctx->plan);
+    for (int i = 0; i < 6; i++) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    cudaFree(ctx->minmax); cudaFree(ctx->sumacc); cudaFree(ctx->sumout);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_frame_free[i]);
+        cudaEventDestroy(ctx->ev_out_ready[i]); cudaEventDestroy(ctx->ev_out_free[i]);
+    }
+    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+    cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+}
+
+const char* ofb_last_error(const ofb_context* ctx) { return ctx ? ctx->err.c_str() : g_error.c_str(); }
+int ofb_device_of(const ofb_context* ctx) { return ctx ? ctx->device : -1; }
+int ofb_sm_count(const ofb_context* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int ofb_synchronize(ofb_context* ctx)
+{
+    if (!ctx) return OFB_ERR_BAD_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->s_h2d));
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_d2h));
+    return OFB_OK;
+}
+
+void* ofb_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void ofb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void* ofb_device_alloc(ofb_context* ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed"; cudaGetLastError(); return nullptr; }
+    return p;
+}
+void ofb_device_free(ofb_context* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+
+int ofb_memcpy_h2d(ofb_context* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return OFB_ERR_BAD_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    return OFB_OK;
+}
+int ofb_memcpy_d2h(ofb_context* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return OFB_ERR_BAD_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    return OFB_OK;
+}
+
+// ---- the drop-in call ---------------------------------------------------------------------------
+int ofb_farneback_device(ofb_context* ctx, const void* d_prev, const void* d_next, int dtype, int W, int H,
+                         size_t prev_pitch, size_t next_pitch, float* d_flow, const ofb_params* p)
+{
+    if (int rc = validate(ctx, W, H, dtype, p)) return rc;
+    if (!d_prev || !d_next || !d_flow) return fail(ctx, OFB_ERR_BAD_ARG, "null frame or flow pointer");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_plan(ctx, W, H, dtype, p)) return rc;
+    size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4);
+    Launch L{ctx->s_compute, &ctx->prof};
+    expand_frame(ctx, L, d_prev, prev_pitch ? prev_pitch : row, 0);
+    expand_frame(ctx, L, d_next, next_pitch ? next_pitch : row, 1);
+    solve_pair(ctx, L, 0, 1, (float2*)d_flow);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    return OFB_OK;
+}
+
+int ofb_farneback_host(ofb_context* ctx, const void* prev, const void* next, int dtype, int W, int H,
+                       size_t prev_pitch, size_t next_pitch, float* flow, const ofb_params* p)
+{
+    if (int rc = validate(ctx, W, H, dtype, p)) return rc;
+    if (!prev || !next || !flow) return fail(ctx, OFB_ERR_BAD_ARG, "null frame or flow pointer");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_plan(ctx, W, H, dtype, p)) return rc;
+    Plan& pl = ctx->plan;
+    cudaStream_t s = ctx->s_compute;
+    if (int rc = upload_frame(ctx, prev, prev_pitch, W, H, dtype, pl.frame[0], s)) return rc;
+    if (int rc = upload_frame(ctx, next, next_pitch, W, H, dtype, pl.frame[1], s)) return rc;
+    size_t fbytes = sizeof(float2) * (size_t)W * H;
+    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) CU(cudaMemcpyAsync(pl.flow0, flow, fbytes, cudaMemcpyHostToDevice, s));
+    size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4);
+    Launch L{s, &ctx->prof};
+    expand_frame(ctx, L, pl.frame[0], row, 0);
+    expand_frame(ctx, L, pl.frame[1], row, 1);
+    solve_pair(ctx, L, 0, 1, pl.flow0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(flow, pl.flow0, fbytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+// ---- companions -------------------------------------------------------------------------------------
+int ofb_flow_to_bgr_device(ofb_context* ctx, const float* d_flow, int W, int H, uint8_t* d_bgr)
+{
+    if (!ctx || !d_flow || !d_bgr || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    Launch L{ctx->s_compute, &ctx->prof};
+    picture(ctx, L, (const float2*)d_flow, (size_t)W * H, d_bgr);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    return OFB_OK;
+}
+
+int ofb_flow_to_bgr_host(ofb_context* ctx, const float* flow, int W, int H, uint8_t* bgr)
+{
+    if (!ctx || !flow || !bgr || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    size_t n = (size_t)W * H;
+    float *df, *db;
+    if (int rc = stage_buf(ctx, 0, n * 8, &df)) return rc;
+    if (int rc = stage_buf(ctx, 1, n * 3 + 16, &db)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
+    Launch L{s, &ctx->prof};
+    picture(ctx, L, (const float2*)df, n, (uint8_t*)db);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(bgr, db, n * 3, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_sum_magnitude_device(ofb_context* ctx, const float* d_flow, int W, int H, float* d_out)
+{
+    if (!ctx || !d_flow || !d_out || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    Launch L{ctx->s_compute, &ctx->prof};
+    launch_sum_magnitude(L, (const float2*)d_flow, (size_t)W * H, ctx->sumacc, d_out);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    return OFB_OK;
+}
+
+int ofb_sum_magnitude_host(ofb_context* ctx, const float* flow, int W, int H, float* out)
+{
+    if (!ctx || !flow || !out || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    size_t n = (size_t)W * H;
+    float* df;
+    if (int rc = stage_buf(ctx, 0, n * 8, &df)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
+    Launch L{s, &ctx->prof};
+    launch_sum_magnitude(L, (const float2*)df, n, ctx->sumacc, ctx->sumout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->sumout, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_cart_to_polar_host(ofb_context* ctx, const float* flow, int W, int H, float* mag, float* ang)
+{
+    if (!ctx || !flow || !mag || !ang || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    size_t n = (size_t)W * H;
+    float *df, *dm, *da;
+    if (int rc = stage_buf(ctx, 0, n * 8, &df)) return rc;
+    if (int rc = stage_buf(ctx, 1, n * 4, &dm)) return rc;
+    if (int rc = stage_buf(ctx, 2, n * 4, &da)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
+    Launch L{s, &ctx->prof};
+    launch_cart_to_polar(L, (const float2*)df, n, dm, da);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(mag, dm, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ang, da, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+// ---- fused pair / shot ------------------------------------------------------------------------------
+int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtype, int W, int H,
+                  const ofb_params* p, uint8_t* bgr, float* magsum, float* flow)
+{
+    if (int rc = validate(ctx, W, H, dtype, p)) return rc;
+    if (!prev || !next) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer");
+    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
+        return fail(ctx, OFB_ERR_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is only meaningful through ofb_farneback_*");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_plan(ctx, W, H, dtype, p)) return rc;
+    Plan& pl = ctx->plan;
+    cudaStream_t s = ctx->s_compute;
+    if (int rc = upload_frame(ctx, prev, 0, W, H, dtype, pl.frame[0], s)) return rc;
+    if (int rc = upload_frame(ctx, next, 0, W, H, dtype, pl.frame[1], s)) return rc;
+    size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4), n = (size_t)W * H;
+    Launch L{s, &ctx->prof};
+    expand_frame(ctx, L, pl.frame[0], row, 0);
+    expand_frame(ctx, L, pl.frame[1], row, 1);
+    solve_pair(ctx, L, 0, 1, pl.flow0);
+    if (bgr) picture(ctx, L, pl.flow0, n, pl.bgr[0]);
+    if (magsum) launch_sum_magnitude(L, pl.flow0, n, ctx->sumacc, ctx->sumout);
+    CU(cudaGetLastError());
+    if (bgr) CU(cudaMemcpyAsync(bgr, pl.bgr[0], n * 3, cudaMemcpyDeviceToHost, s));
+    if (magsum) CU(cudaMemcpyAsync(magsum, ctx->sumout, 4, cudaMemcpyDeviceToHost, s));
+    if (flow) CU(cudaMemcpyAsync(flow, pl.flow0, n * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int W, int H, const ofb_params* p,
+                    uint8_t* d_bgr, float* d_magsum, float* d_flow, float* device_ms)
+{
+    if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
+    if (!d_frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
+    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
+        return fail(ctx, OFB_ERR_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is only meaningful through ofb_farneback_*");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p)) return rc;
+    Plan& pl = ctx->plan;
+    cudaStream_t s = ctx->s_compute;
+    size_t n = (size_t)W * H;
+    Launch L{s, &ctx->prof};
+    CU(cudaEventRecord(ctx->ev_t0, s));
+    expand_frame(ctx, L, d_frames, (size_t)W, 0);
+    for (int t = 0; t + 1 < n_frames; t++) {
+        expand_frame(ctx, L, d_frames + (size_t)(t + 1) * n, (size_t)W, (t + 1) & 1);
+        float2* fl = d_flow ? (float2*)d_flow + (size_t)t * n : pl.flow0;
+        solve_pair(ctx, L, t & 1, (t + 1) & 1, fl);
+        if (d_bgr) picture(ctx, L, fl, n, d_bgr + (size_t)t * n * 3);
+        if (d_magsum) launch_sum_magnitude(L, fl, n, ctx->sumacc, d_magsum + t);
+    }
+    CU(cudaEventRecord(ctx->ev_t1, s));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
+    return OFB_OK;
+}
+
+int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p,
+                  uint8_t* bgr, float* magsum, float* flow, float* device_ms)
+{
+    if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
+    if (!frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
+    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
+        return fail(ctx, OFB_ERR_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is only meaningful through ofb_farneback_*");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p)) return rc;
+    Plan& pl = ctx->plan;
+    cudaStream_t sc = ctx->s_compute, su = ctx->s_h2d, sd = ctx->s_d2h;
+    const size_t n = (size_t)W * H;
+    float* d_sums = nullptr;
+    if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)(n_frames - 1), &d_sums)) return rc;
+    Launch L{sc, &ctx->prof};
+    float2* dflow[2] = {pl.flow0, pl.flow0b};
+
+    CU(cudaEventRecord(ctx->ev_t0, su));
+    // Uploads run ahead on s_h2d (double-buffered device frames), pictures / flows drain on s_d2h
+    // (double-buffered outputs); the compute stream only waits on the events it needs.
+    auto upload = [&](int j) -> int {
+        int b = j & 1;
+        if (j >= 2) CU(cudaStreamWaitEvent(su, ctx->ev_frame_free[b], 0));
+        CU(cudaMemcpyAsync(pl.frame[b], frames + (size_t)j * n, n, cudaMemcpyHostToDevice, su));
+        CU(cudaEventRecord(ctx->ev_h2d[b], su));
+        return 0;
+    };
+    auto expand = [&](int j) -> int {
+        int b = j & 1;
+        CU(cudaStreamWaitEvent(sc, ctx->ev_h2d[b], 0));
+        expand_frame(ctx, L, pl.frame[b], (size_t)W, b);
+        CU(cudaEventRecord(ctx->ev_frame_free[b], sc));
+        return 0;
+    };
+    if (int rc = upload(0)) return rc;
+    if (n_frames > 1) if (int rc = upload(1)) return rc;
+    if (int rc = expand(0)) return rc;
+    for (int t = 0; t + 1 < n_frames; t++) {
+        int b = t & 1;
+        if (int rc = expand(t + 1)) return rc;
+        if (t + 2 < n_frames) if (int rc = upload(t + 2)) return rc;
+        if (t >= 2) CU(cudaStreamWaitEvent(sc, ctx->ev_out_free[b], 0));
+        solve_pair(ctx, L, t & 1, (t + 1) & 1, dflow[b]);
+        if (bgr) picture(ctx, L, dflow[b], n, pl.bgr[b]);
+        if (magsum) launch_sum_magnitude(L, dflow[b], n, ctx->sumacc, d_sums + t);
+        CU(cudaEventRecord(ctx->ev_out_ready[b], sc));
+        CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[b], 0));
+        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t * n * 3, pl.bgr[b], n * 3, cudaMemcpyDeviceToHost, sd));
+        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t * n * 2, dflow[b], n * 8, cudaMemcpyDeviceToHost, sd));
+        CU(cudaEventRecord(ctx->ev_out_free[b], sd));
+    }
+    if (magsum) {
+        CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[(n_frames - 2) & 1], 0));
+        CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)(n_frames - 1), cudaMemcpyDeviceToHost, sd));
+    }
+    CU(cudaEventRecord(ctx->ev_t1, sd));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(sd));
+    CU(cudaStreamSynchronize(sc));
+    CU(cudaStreamSynchronize(su));
+    if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
+    return OFB_OK;
+}
+
+// ---- per-stage entry points ------------------------------------------------------------------------
+int ofb_scale_count(int W, int H, double pyr_scale, int levels) { return num_scales(W, H, pyr_scale, levels); }
+
+int ofb_scale_geometry(int W, int H, double pyr_scale, int k, int* Wk, int* Hk, int* ksize, double* sigma)
+{
+    if (!Wk || !Hk || !ksize || !sigma || k < 0) return OFB_ERR_BAD_ARG;
+    scale_geometry(W, H, pyr_scale, k, Wk, Hk, ksize, sigma, nullptr);
+    return OFB_OK;
+}
+
+int ofb_stage_level_image(ofb_context* ctx, const void* frame, int dtype, int W, int H, double pyr_scale, int k, float* out)
+{
+    if (!ctx || !frame || !out || W <= 0 || H <= 0 || k < 0 || (dtype != OFB_U8 && dtype != OFB_F32))
+        return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    int Wk, Hk, ksize; double sigma;
+    scale_geometry(W, H, pyr_scale, k, &Wk, &Hk, &ksize, &sigma, nullptr);
+    int pitch = round_up(Wk, 32);
+    size_t esz = dtype == OFB_U8 ? 1 : 4;
+    float *dfr, *dT, *dI, *dtaps;
+    if (int rc = stage_buf(ctx, 0, (size_t)W * H * esz, &dfr)) return rc;
+    if (int rc = stage_buf(ctx, 1, sizeof(float) * (size_t)H * pitch, &dT)) return rc;
+    if (int rc = stage_buf(ctx, 2, sizeof(float) * (size_t)Hk * pitch, &dI)) return rc;
+    if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)ksize, &dtaps)) return rc;
+    std::vector<float> taps;
+    gaussian_taps(ksize, sigma, taps);
+    cudaStream_t s = ctx->s_compute;
+    CU(cudaMemcpyAsync(dtaps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dfr, frame, (size_t)W * H * esz, cudaMemcpyHostToDevice, s));
+    Launch L{s, &ctx->prof};
+    launch_pyr_h(L, dfr, dtype, W, H, (size_t)W * esz, dtaps, ksize, dT, Wk, pitch);
+    launch_pyr_v(L, dT, H, pitch, dtaps, ksize, dI, Wk, Hk, pitch);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2DAsync(out, sizeof(float) * Wk, dI, sizeof(float) * pitch, sizeof(float) * Wk, Hk, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_stage_polyexp(ofb_context* ctx, const float* img, int W, int H, int poly_n, double poly_sigma, float* R)
+{
+    if (!ctx || !img || !R || W <= 0 || H <= 0 || poly_n < 1 || poly_n > 64) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    int pitch = round_up(W, 32);
+    size_t plane = (size_t)H * pitch;
+    float *dI, *dtmp, *dR, *dout, *dtab;
+    if (int rc = stage_buf(ctx, 0, sizeof(float) * plane, &dI)) return rc;
+    if (int rc = stage_buf(ctx, 1, sizeof(float) * 3 * plane, &dtmp)) return rc;
+    if (int rc = stage_buf(ctx, 2, sizeof(float) * 5 * plane, &dR)) return rc;
+    if (int rc = stage_buf(ctx, 3, sizeof(float) * 5 * (size_t)W * H, &dout)) return rc;
+    std::vector<float> tab; double ig[4];
+    poly_constants(poly_n, poly_sigma, tab, ig);
+    if (int rc = stage_buf(ctx, 4, sizeof(float) * tab.size(), &dtab)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    CU(cudaMemcpyAsync(dtab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(dI, sizeof(float) * pitch, img, sizeof(float) * W, sizeof(float) * W, H, cudaMemcpyHostToDevice, s));
+    int len = 2 * poly_n + 1;
+    PolyConst pc{dtab, dtab + len, dtab + 2 * len, poly_n, ig[0], ig[1], ig[2], ig[3]};
+    Launch L{s, &ctx->prof};
+    Planes5 Rp{dR, plane, pitch};
+    launch_polyexp(L, dI, W, H, pitch, pc, dtmp, Rp, ctx->generic);
+    launch_interleave5(L, Rp, W, H, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(R, dout, sizeof(float) * 5 * (size_t)W * H, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_stage_update_matrices(ofb_context* ctx, const float* R0, const float* R1, const float* flow, int W, int H, float* M)
+{
+    if (!ctx || !R0 || !R1 || !flow || !M || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    int pitch = round_up(W, 32);
+    size_t plane = (size_t)H * pitch, n = (size_t)W * H;
+    float *din, *dR0, *dR1, *dM, *dfl;
+    if (int rc = stage_buf(ctx, 0, sizeof(float) * 5 * n, &din)) return rc;
+    if (int rc = stage_buf(ctx, 1, sizeof(float) * 5 * plane, &dR0)) return rc;
+    if (int rc = stage_buf(ctx, 2, sizeof(float) * 5 * plane, &dR1)) return rc;
+    if (int rc = stage_buf(ctx, 3, sizeof(float) * 5 * plane, &dM)) return rc;
+    if (int rc = stage_buf(ctx, 4, sizeof(float) * 2 * n, &dfl)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    Launch L{s, &ctx->prof};
+    Planes5 p0{dR0, plane, pitch}, p1{dR1, plane, pitch}, pm{dM, plane, pitch};
+    CU(cudaMemcpyAsync(din, R0, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
+    launch_deinterleave5(L, din, W, H, p0);
+    CU(cudaMemcpyAsync(din, R1, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
+    launch_deinterleave5(L, din, W, H, p1);
+    CU(cudaMemcpyAsync(dfl, flow, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
+    launch_update_matrices(L, p0, p1, (const float2*)dfl, W, H, pm);
+    launch_interleave5(L, pm, W, H, din);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(M, din, sizeof(float) * 5 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_stage_blur_solve(ofb_context* ctx, const float* M, int W, int H, int winsize, int gaussian, float* flow)
+{
+    if (!ctx || !M || !flow || W <= 0 || H <= 0 || winsize < 1 || winsize > 1024) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    int pitch = round_up(W, 32);
+    size_t plane = (size_t)H * pitch, n = (size_t)W * H;
+    float *din, *dM, *dtmp, *dfl, *dk;
+    if (int rc = stage_buf(ctx, 0, sizeof(float) * 5 * n, &din)) return rc;
+    if (int rc = stage_buf(ctx, 1, sizeof(float) * 5 * plane, &dM)) return rc;
+    if (int rc = stage_buf(ctx, 2, sizeof(double) * 5 * plane, &dtmp)) return rc;
+    if (int rc = stage_buf(ctx, 3, sizeof(float) * 2 * n, &dfl)) return rc;
+    std::vector<float> gk;
+    gauss_half_taps(winsize, gk);
+    if (int rc = stage_buf(ctx, 4, sizeof(float) * gk.size(), &dk)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    Launch L{s, &ctx->prof};
+    Planes5 pm{dM, plane, pitch};
+    CU(cudaMemcpyAsync(dk, gk.data(), sizeof(float) * gk.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(din, M, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
+    launch_deinterleave5(L, din, W, H, pm);
+    if (gaussian) launch_blur_solve_gauss(L, pm, W, H, winsize, dk, dtmp, (float2*)dfl, ctx->generic);
+    else launch_blur_solve_box(L, pm, W, H, winsize, (double*)dtmp, (float2*)dfl, ctx->generic);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(flow, dfl, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, int Hp, int W, int H, double pyr_scale, float* flow)
+{
+    if (!ctx || !prev_flow || !flow || W <= 0 || H <= 0 || Wp <= 0 || Hp <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    float *dp, *df;
+    if (int rc = stage_buf(ctx, 0, sizeof(float) * 2 * (size_t)Wp * Hp, &dp)) return rc;
+    if (int rc = stage_buf(ctx, 1, sizeof(float) * 2 * (size_t)W * H, &df)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    Launch L{s, &ctx->prof};
+    CU(cudaMemcpyAsync(dp, prev_flow, sizeof(float) * 2 * (size_t)Wp * Hp, cudaMemcpyHostToDevice, s));
+    launch_upsample_flow(L, (const float2*)dp, Wp, Hp, (float2*)df, W, H, (float)(1. / pyr_scale));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(flow, df, sizeof(float) * 2 * (size_t)W * H, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+// ---- options and measurement -----------------------------------------------------------------------
+int ofb_set_option(ofb_context* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return OFB_ERR_BAD_ARG;
+    if (!strcmp(name, "generic_kernels")) { ctx->generic = value != 0; return OFB_OK; }
+    if (!strcmp(name, "profile")) {
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        ctx->prof.collect();
+        ctx->prof.timing = value != 0;
+        return OFB_OK;
+    }
+    return fail(ctx, OFB_ERR_BAD_ARG, std::string("unknown option: ") + name);
+}
+
+int ofb_get_kernel_stats(ofb_context* ctx, ofb_kernel_stat* out, int max)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    ctx->prof.collect();
+    int n = (int)ctx->prof.stats.size();
+    for (int i = 0; i < n && i < max && out; i++) {
+        memset(&out[i], 0, sizeof(out[i]));
+        strncpy(out[i].name, ctx->prof.stats[i].name.c_str(), sizeof(out[i].name) - 1);
+        out[i].launches = ctx->prof.stats[i].launches;
+        out[i].total_ms = ctx->prof.stats[i].total_ms;
+    }
+    return n;
+}
+
+void ofb_reset_kernel_stats(ofb_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->prof.reset();
+}
+
+double ofb_algorithmic_bytes_pair(int W, int H, const ofb_params* p)
+{
+    if (!p || W <= 0 || H <= 0 || !(p->pyr_scale < 1) || !(p->pyr_scale > 0)) return 0;
+    int K = num_scales(W, H, p->pyr_scale, p->levels);
+    double N = (double)W * H, total = 0, prevNk = 0;
+    for (int k = K; k >= 0; k--) {
+        int Wk, Hk, ks; double sg;
+        scale_geometry(W, H, p->pyr_scale, k, &Wk, &Hk, &ks, &sg, nullptr);
+        double Nk = (double)Wk * Hk;
+        total += 2 * N + (64.0 + 96.0 * p->iterations) * Nk + 8.0 * prevNk;
+        prevNk = Nk;
+    }
+    return total;
+}
+
+double ofb_algorithmic_bytes_viz(int W, int H) { return 19.0 * (double)W * H; }
+
+#pragma GCC visibility pop
+}  // extern "C"

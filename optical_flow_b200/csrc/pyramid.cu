@@ -1,0 +1,103 @@
+// pyramid.cu -- level image I_k of SURVEY.md A.3, the per-frame front of cv2.calcOpticalFlowFarneback
+// (call sites /root/reference/optical_flow.py:51, visualize_optical_flow.py:38):
+//     convertTo(CV_32F) -> GaussianBlur(ksize_k, sigma_k, reflect-101) -> resize(INTER_LINEAR)
+// always taken from the FULL-RESOLUTION frame.
+//
+// cv2 blurs the whole frame and then samples it; only the two blurred columns / rows that the
+// bilinear sample touches are needed, and the four linear, separable operators commute
+// (Vlerp o Hlerp o Vblur o Hblur == [Vlerp o Vblur] o [Hlerp o Hblur]).  So:
+//   k_pyr_h : T(r, x)   = (1-ax) * Hblur(r, sx) + ax * Hblur(r, sx+1)      for all H source rows
+//   k_pyr_v : I(y, x)   = (1-ay) * Vblur_T(sy, x) + ay * Vblur_T(sy+1, x)
+// Work is O(H*W_k*ksize) instead of O(H*W*ksize) per level.  f32 taps, f32 accumulation, taps
+// applied left-to-right (the order of the CPU oracle, oracle/farneback_oracle.c gaussian_blur_f32).
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace ofb {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pyr_h(const T* __restrict__ src, int W, int H, size_t pitch_bytes, const float* __restrict__ taps, int ksize,
+        double scale_x, float* __restrict__ dst, int Wk, int dst_pitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= Wk || r >= H) return;
+    float a1;
+    int sx = linear_coord(x, scale_x, W, &a1);
+    float a0 = 1.f - a1;
+    const T* row = (const T*)((const char*)src + (size_t)r * pitch_bytes);
+    int c = ksize / 2;
+    float b0 = 0.f, b1 = 0.f;
+    if (sx - c >= 0 && sx + 1 + c < W) {            // interior: no border arithmetic
+        const T* p = row + sx - c;
+        if (a1 != 0.f) {
+            float prev = (float)p[0];
+            for (int j = 0; j < ksize; j++) {
+                float cur = (float)p[j + 1];
+                float t = __ldg(taps + j);
+                b0 += t * prev;
+                b1 += t * cur;
+                prev = cur;
+            }
+        } else {
+            for (int j = 0; j < ksize; j++) b0 += __ldg(taps + j) * (float)p[j];
+        }
+    } else {
+        int sx1 = min(sx + 1, W - 1);
+        for (int j = 0; j < ksize; j++) {
+            float t = __ldg(taps + j);
+            b0 += t * (float)row[reflect101(sx + j - c, W)];
+            if (a1 != 0.f) b1 += t * (float)row[reflect101(sx1 + j - c, W)];
+        }
+    }
+    dst[(size_t)r * dst_pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
+}
+
+__global__ void __launch_bounds__(256)
+k_pyr_v(const float* __restrict__ T, int H, int t_pitch, const float* __restrict__ taps, int ksize,
+        double scale_y, float* __restrict__ dst, int Wk, int Hk, int dst_pitch)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= Wk || y >= Hk) return;
+    float a1;
+    int sy = linear_coord(y, scale_y, H, &a1);
+    float a0 = 1.f - a1;
+    int sy1 = min(sy + 1, H - 1);
+    int c = ksize / 2;
+    float b0 = 0.f, b1 = 0.f;
+    for (int j = 0; j < ksize; j++) {
+        float t = __ldg(taps + j);
+        b0 += t * T[(size_t)reflect101(sy + j - c, H) * t_pitch + x];
+        if (a1 != 0.f) b1 += t * T[(size_t)reflect101(sy1 + j - c, H) * t_pitch + x];
+    }
+    dst[(size_t)y * dst_pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
+}
+
+void launch_pyr_h(Launch& L, const void* frame, int dtype, int W, int H, size_t pitch_bytes,
+                  const float* taps, int ksize, float* T, int Wk, int t_pitch)
+{
+    dim3 block(64, 4), grid(divup(Wk, 64), divup(H, 4));
+    double scale_x = 1.0 / ((double)Wk / W);
+    if (dtype == 0)
+        L.run("pyr_h_u8", [&](cudaStream_t s) {
+            k_pyr_h<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)frame, W, H, pitch_bytes, taps, ksize, scale_x, T, Wk, t_pitch);
+        });
+    else
+        L.run("pyr_h_f32", [&](cudaStream_t s) {
+            k_pyr_h<float><<<grid, block, 0, s>>>((const float*)frame, W, H, pitch_bytes, taps, ksize, scale_x, T, Wk, t_pitch);
+        });
+}
+
+void launch_pyr_v(Launch& L, const float* T, int H, int t_pitch, const float* taps, int ksize,
+                  float* I, int Wk, int Hk, int i_pitch)
+{
+    dim3 block(64, 4), grid(divup(Wk, 64), divup(Hk, 4));
+    double scale_y = 1.0 / ((double)Hk / H);
+    L.run("pyr_v", [&](cudaStream_t s) {
+        k_pyr_v<<<grid, block, 0, s>>>(T, H, t_pitch, taps, ksize, scale_y, I, Wk, Hk, i_pitch);
+    });
+}
+
+}  // namespace ofb

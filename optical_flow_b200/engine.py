@@ -1,0 +1,312 @@
+"""Host-side mirror of the reference's operator interface for the Farneback + HSV hot path.
+
+`Farneback` owns one C-ABI context (one GPU, its streams and workspaces).  The module-level functions in
+`optical_flow_b200/__init__.py` (`calcOpticalFlowFarneback`, `cartToPolar`) keep cv2's names, argument
+meaning and error behaviour so that the two call sites of the reference,
+/root/reference/optical_flow.py:51-64 and /root/reference/visualize_optical_flow.py:38-55, can switch
+by changing one import.
+
+No CPU fallback: every method runs CUDA kernels through include/optflow_b200.h or raises.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+OPTFLOW_USE_INITIAL_FLOW = 4
+OPTFLOW_FARNEBACK_GAUSSIAN = 256
+
+#: the seven literals hard-coded at optical_flow.py:53-59 and visualize_optical_flow.py:40-46
+REFERENCE_PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+
+_ASSERT_FRAMES = ("prev0.size() == next0.size() && prev0.channels() == next0.channels() && "
+                  "prev0.channels() == 1 && pyrScale_ < 1")
+_ASSERT_FLOW = "_flow0.size() == prev0.size() && _flow0.channels() == 2 && _flow0.depth() == CV_32F"
+
+
+class error(Exception):
+    """Mirror of cv2.error for the argument errors of calcOpticalFlowFarneback (code -215)."""
+
+    def __init__(self, msg, code=-215, func="calc"):
+        super().__init__("OpenCV-compatible(%d) error: (%d:Assertion failed) %s in function '%s'" % (code, code, msg, func))
+        self.code = code
+        self.err = msg
+        self.func = func
+        self.msg = str(self)
+
+
+def make_params(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0):
+    return _lib.Params(float(pyr_scale), int(levels), int(winsize), int(iterations), int(poly_n), float(poly_sigma), int(flags))
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array backed by page-locked host memory (cudaHostAlloc), for overlapped H2D / D2H."""
+    L = _lib.load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = L.ofb_host_alloc(max(n, 1))
+    if not p:
+        raise MemoryError("cudaHostAlloc(%d bytes) failed" % n)
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, L.ofb_host_free, p)
+    return arr
+
+
+def _single_channel(a, name):
+    a = np.asarray(a)
+    if a.ndim == 3 and a.shape[2] == 1:
+        a = a[..., 0]
+    if a.ndim != 2:
+        raise error(_ASSERT_FRAMES)
+    return a
+
+
+def _as_frame(a):
+    """cv2 converts any depth to f32 first: u8 goes to the u8 kernels, the rest via f32."""
+    if a.dtype == np.uint8:
+        return np.ascontiguousarray(a), _lib.OFB_U8
+    if a.dtype.kind in "uifb":
+        return np.ascontiguousarray(a, dtype=np.float32), _lib.OFB_F32
+    raise TypeError("unsupported frame dtype %s" % a.dtype)
+
+
+def validate_call(prev, next, flow, pyr_scale, flags):
+    """Argument contract of cv2.calcOpticalFlowFarneback, GPU-free:
+    returns (prev, next, dtype_code, out_flow) or raises `error` with cv2's -215 texts."""
+    prev = _single_channel(prev, "prev")
+    next = _single_channel(next, "next")
+    if prev.shape != next.shape or not (float(pyr_scale) < 1):
+        raise error(_ASSERT_FRAMES)
+    H, W = prev.shape
+    flags = int(flags)
+    good = isinstance(flow, np.ndarray) and flow.dtype == np.float32 and flow.shape == (H, W, 2)
+    inplace = good and flow.flags.c_contiguous and flow.flags.writeable
+    if flags & OPTFLOW_USE_INITIAL_FLOW:
+        if not good:
+            raise error(_ASSERT_FLOW)
+        out = flow if inplace else np.ascontiguousarray(flow).copy()
+    else:
+        out = flow if inplace else np.empty((H, W, 2), np.float32)   # a wrong `flow` is silently ignored (8b)
+    p, dt = _as_frame(prev)
+    n, dt2 = _as_frame(next)
+    if dt != dt2:                                                  # cv2 accepts mixed depths
+        p, n, dt = p.astype(np.float32), n.astype(np.float32), _lib.OFB_F32
+    return p, n, dt, out
+
+
+class Farneback:
+    """One engine context on one GPU (C-ABI: ofb_create / ofb_destroy)."""
+
+    def __init__(self, device=0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.ofb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("optical_flow_b200: cannot create engine on device %d: %s (status %d)"
+                               % (device, self._L.ofb_global_error().decode(), rc))
+        self._h = h
+        self.device = int(device)
+        self._fin = weakref.finalize(self, self._L.ofb_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _check(self, rc, func="calc"):
+        if rc == 0:
+            return
+        msg = self._L.ofb_last_error(self._h).decode()
+        if rc == _lib.OFB_ERR_ASSERT:
+            raise error(msg, func=func)
+        if rc == _lib.OFB_ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        if rc == _lib.OFB_ERR_BAD_ARG:
+            raise ValueError(msg)
+        raise RuntimeError("optical_flow_b200 CUDA failure (%d): %s" % (rc, msg))
+
+    @property
+    def sm_count(self):
+        return self._L.ofb_sm_count(self._h)
+
+    def set_option(self, name, value):
+        self._check(self._L.ofb_set_option(self._h, name.encode(), int(value)))
+
+    def synchronize(self):
+        self._check(self._L.ofb_synchronize(self._h))
+
+    def kernel_stats(self):
+        arr = (_lib.KernelStat * 128)()
+        n = self._L.ofb_get_kernel_stats(self._h, arr, 128)
+        return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].total_ms)) for i in range(min(n, 128))}
+
+    def reset_kernel_stats(self):
+        self._L.ofb_reset_kernel_stats(self._h)
+
+    # -- the drop-in call ----------------------------------------------------------------------------
+    def calc(self, prev, next, flow, pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags):
+        """cv2.calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, iterations, poly_n,
+        poly_sigma, flags) -> flow   (optical_flow.py:51-59, visualize_optical_flow.py:38-46)."""
+        p, n, dt, out = validate_call(prev, next, flow, pyr_scale, flags)
+        H, W = p.shape
+        prm = make_params(pyr_scale, levels, winsize, iterations, poly_n, poly_sigma, flags)
+        self._check(self._L.ofb_farneback_host(self._h, _ptr(p), _ptr(n), dt, W, H, 0, 0, _ptr(out), C.byref(prm)))
+        return out
+
+    # -- companions ----------------------------------------------------------------------------------
+    def cart_to_polar(self, flow):
+        """cv2.cartToPolar(flow[...,0], flow[...,1]) -> (magnitude, angle[rad])."""
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        H, W = flow.shape[:2]
+        mag = np.empty((H, W), np.float32)
+        ang = np.empty((H, W), np.float32)
+        self._check(self._L.ofb_cart_to_polar_host(self._h, _ptr(flow), W, H, _ptr(mag), _ptr(ang)), "cartToPolar")
+        return mag, ang
+
+    def sum_magnitude(self, flow):
+        """np.sum(cv2.cartToPolar(...)[0])  (optical_flow.py:61-64)."""
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        H, W = flow.shape[:2]
+        out = np.zeros(1, np.float32)
+        self._check(self._L.ofb_sum_magnitude_host(self._h, _ptr(flow), W, H, _ptr(out)))
+        return np.float32(out[0])
+
+    def flow_to_bgr(self, flow):
+        """The HSV picture of visualize_optical_flow.py:48-55 as one fused GPU pass."""
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        H, W = flow.shape[:2]
+        bgr = np.empty((H, W, 3), np.uint8)
+        self._check(self._L.ofb_flow_to_bgr_host(self._h, _ptr(flow), W, H, _ptr(bgr)))
+        return bgr
+
+    # -- fused pair / shot ---------------------------------------------------------------------------
+    def pair(self, prev, next, want_bgr=True, want_magsum=False, want_flow=False, **params):
+        """One loop body of the reference: frames in, picture and/or summed magnitude out; the f32 flow
+        stays on the GPU unless want_flow."""
+        prev = _single_channel(prev, "prev")
+        next = _single_channel(next, "next")
+        if prev.shape != next.shape:
+            raise error(_ASSERT_FRAMES)
+        H, W = prev.shape
+        p, dt = _as_frame(prev)
+        n, dt2 = _as_frame(next)
+        if dt != dt2:
+            p, n, dt = p.astype(np.float32), n.astype(np.float32), _lib.OFB_F32
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        bgr = np.empty((H, W, 3), np.uint8) if want_bgr else None
+        ms = np.zeros(1, np.float32) if want_magsum else None
+        fl = np.empty((H, W, 2), np.float32) if want_flow else None
+        self._check(self._L.ofb_pair_host(self._h, _ptr(p), _ptr(n), dt, W, H, C.byref(prm), _ptr(bgr), _ptr(ms), _ptr(fl)))
+        return {"bgr": bgr, "magsum": None if ms is None else np.float32(ms[0]), "flow": fl}
+
+    def shot(self, frames, want_bgr=True, want_magsum=False, want_flow=False, out_bgr=None, **params):
+        """All consecutive pairs of a shot: frames (n, H, W) uint8 -> n-1 results.  Per-frame work is
+        shared between the two pairs of each frame; uploads / downloads overlap compute."""
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim != 3 or frames.dtype != np.uint8 or frames.shape[0] < 2:
+            raise ValueError("frames must be (n>=2, H, W) uint8")
+        n, H, W = frames.shape
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        bgr = None
+        if want_bgr:
+            bgr = out_bgr if out_bgr is not None else np.empty((n - 1, H, W, 3), np.uint8)
+            assert bgr.shape == (n - 1, H, W, 3) and bgr.dtype == np.uint8 and bgr.flags.c_contiguous
+        ms = np.zeros(n - 1, np.float32) if want_magsum else None
+        fl = np.empty((n - 1, H, W, 2), np.float32) if want_flow else None
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_shot_host(self._h, _ptr(frames), n, W, H, C.byref(prm), _ptr(bgr), _ptr(ms), _ptr(fl),
+                                          C.byref(dev_ms)))
+        return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
+
+    # -- device-resident shot (bench: inputs already in HBM) -------------------------------------------
+    def device_alloc(self, nbytes):
+        p = self._L.ofb_device_alloc(self._h, int(nbytes))
+        if not p:
+            raise MemoryError("cudaMalloc(%d) failed" % nbytes)
+        return p
+
+    def device_free(self, p):
+        self._L.ofb_device_free(self._h, C.c_void_p(p))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self._L.ofb_memcpy_h2d(self._h, C.c_void_p(dptr), _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        assert arr.flags.c_contiguous
+        self._check(self._L.ofb_memcpy_d2h(self._h, _ptr(arr), C.c_void_p(dptr), arr.nbytes))
+
+    def shot_device(self, d_frames, n_frames, W, H, d_bgr=None, d_magsum=None, d_flow=None, **params):
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_shot_device(self._h, C.c_void_p(d_frames), int(n_frames), W, H, C.byref(prm),
+                                            C.c_void_p(d_bgr), C.c_void_p(d_magsum), C.c_void_p(d_flow), C.byref(dev_ms)))
+        return float(dev_ms.value)
+
+    # -- per-stage entry points (parity tests) ---------------------------------------------------------
+    def stage_level_image(self, frame, pyr_scale, k):
+        f, dt = _as_frame(_single_channel(frame, "frame"))
+        H, W = f.shape
+        wk, hk, ks = C.c_int(), C.c_int(), C.c_int()
+        sg = C.c_double()
+        self._L.ofb_scale_geometry(W, H, float(pyr_scale), int(k), C.byref(wk), C.byref(hk), C.byref(ks), C.byref(sg))
+        out = np.empty((hk.value, wk.value), np.float32)
+        self._check(self._L.ofb_stage_level_image(self._h, _ptr(f), dt, W, H, float(pyr_scale), int(k), _ptr(out)))
+        return out
+
+    def stage_polyexp(self, img, poly_n, poly_sigma):
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        H, W = img.shape
+        R = np.empty((H, W, 5), np.float32)
+        self._check(self._L.ofb_stage_polyexp(self._h, _ptr(img), W, H, int(poly_n), float(poly_sigma), _ptr(R)))
+        return R
+
+    def stage_update_matrices(self, R0, R1, flow):
+        R0 = np.ascontiguousarray(R0, dtype=np.float32)
+        R1 = np.ascontiguousarray(R1, dtype=np.float32)
+        flow = np.ascontiguousarray(flow, dtype=np.float32)
+        H, W = flow.shape[:2]
+        M = np.empty((H, W, 5), np.float32)
+        self._check(self._L.ofb_stage_update_matrices(self._h, _ptr(R0), _ptr(R1), _ptr(flow), W, H, _ptr(M)))
+        return M
+
+    def stage_blur_solve(self, M, winsize, gaussian=False):
+        M = np.ascontiguousarray(M, dtype=np.float32)
+        H, W = M.shape[:2]
+        flow = np.empty((H, W, 2), np.float32)
+        self._check(self._L.ofb_stage_blur_solve(self._h, _ptr(M), W, H, int(winsize), int(bool(gaussian)), _ptr(flow)))
+        return flow
+
+    def stage_upsample_flow(self, prev_flow, W, H, pyr_scale):
+        prev_flow = np.ascontiguousarray(prev_flow, dtype=np.float32)
+        Hp, Wp = prev_flow.shape[:2]
+        flow = np.empty((H, W, 2), np.float32)
+        self._check(self._L.ofb_stage_upsample_flow(self._h, _ptr(prev_flow), Wp, Hp, W, H, float(pyr_scale), _ptr(flow)))
+        return flow
+
+
+def scale_schedule(W, H, pyr_scale, levels):
+    """[(k, W_k, H_k, ksize_k, sigma_k)] for k = K..0, computed by the C library."""
+    L = _lib.load()
+    K = L.ofb_scale_count(W, H, float(pyr_scale), int(levels))
+    out = []
+    for k in range(K, -1, -1):
+        wk, hk, ks = C.c_int(), C.c_int(), C.c_int()
+        sg = C.c_double()
+        L.ofb_scale_geometry(W, H, float(pyr_scale), k, C.byref(wk), C.byref(hk), C.byref(ks), C.byref(sg))
+        out.append((k, wk.value, hk.value, ks.value, sg.value))
+    return out
+
+
+def algorithmic_bytes(W, H, with_viz=True, **params):
+    """compulsory HBM bytes of one frame pair (B_pair, plus B_viz = 19*W*H)."""
+    L = _lib.load()
+    prm = make_params(**{**REFERENCE_PARAMS, **params})
+    b = L.ofb_algorithmic_bytes_pair(W, H, C.byref(prm))
+    return b + (L.ofb_algorithmic_bytes_viz(W, H) if with_viz else 0.0)

@@ -1,0 +1,130 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol of include/optflow_b200.h, the host
+side mirrors cv2's argument contract, scale schedule / byte model / sharding logic."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import optical_flow_b200 as ofb
+from optical_flow_b200 import _lib
+from optical_flow_b200.engine import validate_call
+from conftest import ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "optflow_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(ofb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    L = _lib.load()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.ofb_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    L = _lib.load()
+    if L.ofb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ofb.Farneback(0)
+
+
+def test_product_never_imports_the_oracle_or_cv2_compute():
+    pkg = os.path.join(ROOT, "optical_flow_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "liboracle" not in src, f
+                assert "cv2.calcOpticalFlowFarneback(" not in src.replace("cv2.calcOpticalFlowFarneback(prev", ""), f
+
+
+def test_scale_schedule_matches_oracle(oracle):
+    for (W, H, ps, lv) in [(1920, 1080, 0.5, 3), (3840, 2160, 0.5, 5), (129, 77, 0.5, 3), (480, 270, 0.7, 4),
+                           (40, 40, 0.5, 3), (640, 360, 0.5, 0), (640, 360, 0.5, -1), (33, 65, 0.5, 3)]:
+        a = ofb.scale_schedule(W, H, ps, lv)
+        b = [(k, w, h, ks, sg) for (k, w, h, ks, sg, _) in oracle.scale_schedule(W, H, ps, lv)]
+        assert a == b
+
+
+def test_algorithmic_bytes_match_survey_8d():
+    mb = lambda **kw: ofb.algorithmic_bytes(with_viz=False, **kw) / 1e6
+    assert abs(mb(W=1920, H=1080) - 991.4) < 0.1
+    assert abs(mb(W=640, H=360) - 110.2) < 0.1
+    assert abs(mb(W=1280, H=720) - 440.6) < 0.1
+    assert abs(mb(W=1280, H=720, iterations=10) - 1263.2) < 0.2
+    assert abs(mb(W=1920, H=1080, iterations=10) - 2842.1) < 0.2
+    assert abs(mb(W=3840, H=2160, levels=5) - 4013.5) < 0.2
+    assert abs(ofb.algorithmic_bytes(1920, 1080) / 1e6 - (991.4 + 39.4)) < 0.1
+
+
+def test_validate_call_errors_mirror_cv2():
+    a = np.zeros((40, 50), np.uint8)
+    with pytest.raises(ofb.error) as e:
+        validate_call(a, np.zeros((40, 51), np.uint8), None, 0.5, 0)
+    assert e.value.code == -215 and "prev0.size() == next0.size()" in str(e.value)
+    with pytest.raises(ofb.error):
+        validate_call(np.zeros((40, 50, 3), np.uint8), np.zeros((40, 50, 3), np.uint8), None, 0.5, 0)
+    with pytest.raises(ofb.error):
+        validate_call(a, a, None, 1.0, 0)
+    with pytest.raises(ofb.error) as e:
+        validate_call(a, a, None, 0.5, ofb.OPTFLOW_USE_INITIAL_FLOW)
+    assert "_flow0.size() == prev0.size()" in str(e.value)
+    with pytest.raises(ofb.error):
+        validate_call(a, a, np.zeros((40, 50, 2), np.float64), 0.5, ofb.OPTFLOW_USE_INITIAL_FLOW)
+
+
+def test_validate_call_flow_ownership_and_depths():
+    a = np.zeros((40, 50), np.uint8)
+    good = np.zeros((40, 50, 2), np.float32)
+    p, n, dt, out = validate_call(a, a, good, 0.5, 0)
+    assert out is good and dt == _lib.OFB_U8
+    # wrong flow silently ignored without the flag
+    for bad in (np.zeros((40, 50, 2), np.float64), np.zeros((10, 10, 2), np.float32), None):
+        _, _, _, out = validate_call(a, a, bad, 0.5, 0)
+        assert out is not bad and out.shape == (40, 50, 2) and out.dtype == np.float32
+    # any depth is accepted and routed through f32; mixed depths too; views are copied
+    for dt_in in (np.uint16, np.int16, np.float32, np.float64):
+        p, n, dt, _ = validate_call(a.astype(dt_in), a.astype(dt_in), None, 0.5, 0)
+        assert dt == _lib.OFB_F32 and p.dtype == np.float32
+    p, n, dt, _ = validate_call(a, a.astype(np.float64), None, 0.5, 0)
+    assert dt == _lib.OFB_F32 and p.dtype == np.float32 and n.dtype == np.float32
+    big = np.zeros((80, 100), np.uint8)
+    p, n, dt, _ = validate_call(big[::2, ::2], big[::2, ::2], None, 0.5, 0)
+    assert p.flags.c_contiguous and p.shape == (40, 50)
+    p, _, _, _ = validate_call(a[..., None], a[..., None], None, 0.5, 0)
+    assert p.shape == (40, 50)
+
+
+def test_shard_pairs_cover_exactly_once():
+    for n in (0, 1, 7, 300, 20000):
+        for ws in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(ws):
+                s, e = ofb.shard_pairs(n, ws, r)
+                assert 0 <= s <= e <= n
+                got += list(range(s, e))
+            assert got == list(range(n))
+            sizes = [ofb.shard_pairs(n, ws, r)[1] - ofb.shard_pairs(n, ws, r)[0] for r in range(ws)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_shots_balanced_and_complete():
+    rng = np.random.default_rng(0)
+    lengths = rng.integers(50, 401, 80).tolist()
+    for ws in (1, 2, 4, 8):
+        parts = ofb.shard_shots(lengths, ws)
+        seen = {}
+        loads = []
+        for r in parts:
+            loads.append(sum(p[2] for p in r))
+            for (i, off, n) in r:
+                for t in range(off, off + n):
+                    assert (i, t) not in seen
+                    seen[(i, t)] = 1
+        assert len(seen) == sum(lengths)
+        assert max(loads) - min(loads) <= max(lengths)
+    parts = ofb.shard_shots([1000], 4)
+    assert sorted(p for r in parts for p in r) == [(0, 0, 250), (0, 250, 250), (0, 500, 250), (0, 750, 250)]
