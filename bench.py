@@ -36,13 +36,14 @@ PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_
 
 # algorithmic HBM bytes per pixel of a launch, per kernel (SURVEY.md 8d stage model)
 KERNEL_BYTES_PER_PX = {
-    "polyexp_tiled": 24.0,        # 4 read I + 20 write R            (per level pixel)
-    "update_matrices": 68.0,      # 20 + 20 + 8 read, 20 write
-    "box_strip": 28.0,            # 20 read M, 8 write flow
+    "polyexp_scale0": 29.0,       # scale 0: 1 read frame + (4 write + 4 read I, fused away) + 20 write R
+    "polyexp_level": 24.0,        # 4 read I + 20 write R            (per level pixel)
+    "um0_zero": 68.0,             # UpdateMatrices: 20 + 20 + 8 read, 20 write
+    "um0_upsample": 76.0,         # + the 8 B/px flow initialisation it absorbs
     "iter_fused": 96.0,           # blur+solve (28) + UpdateMatrices (68) in one launch
+    "iter_last": 28.0,            # 20 read M, 8 write flow
     "minmax_mag": 8.0,            # per frame pixel
     "flow_to_bgr_v4": 11.0,       # 8 read flow + 3 write picture
-    "upsample_flow": 8.0,
 }
 
 
@@ -209,6 +210,10 @@ def run_ours(args, rank, local_rank, world):
     W, H, P = args.width, args.height, args.pairs
     n = W * H
     eng = ofb.Farneback(local_rank)          # raises if the CUDA library / device is missing: no fallback
+    if args.batch > 0:
+        eng.set_option("batch", args.batch)
+    if args.batch_scale0 >= 0:
+        eng.set_option("batch_scale0", args.batch_scale0)
     try:
         import torch
         torch.cuda.set_device(local_rank)
@@ -277,17 +282,19 @@ def run_ours(args, rank, local_rank, world):
         peak, peak_src = peaks()
         sched = ofb.scale_schedule(W, H, PARAMS["pyr_scale"], PARAMS["levels"])
         sum_nk = float(sum(w * h for (_, w, h, _, _) in sched))
-        px_per_launch_total = {   # pixels processed by ALL launches of the kernel in one pair
-            "polyexp_tiled": sum_nk, "update_matrices": sum_nk * PARAMS["iterations"],
-            "box_strip": sum_nk * PARAMS["iterations"], "iter_fused": sum_nk * (PARAMS["iterations"] - 1),
+        n0 = float(sched[-1][1] * sched[-1][2])          # scale-0 pixels
+        nK = float(sched[0][1] * sched[0][2])            # coarsest-scale pixels
+        px_per_launch_total = {   # pixels processed by ALL launches of the kernel for one pair (or frame)
+            "polyexp_scale0": n0, "polyexp_level": sum_nk - n0,
+            "um0_zero": nK, "um0_upsample": sum_nk - nK,
+            "iter_fused": sum_nk * (PARAMS["iterations"] - 1), "iter_last": sum_nk,
             "minmax_mag": float(n), "flow_to_bgr_v4": float(n),
-            "upsample_flow": sum_nk - float(sched[0][1] * sched[0][2]),
         }
         tot_ms = sum(v[1] for v in stats.values())
         for name, (cnt, ms) in sorted(stats.items(), key=lambda kv: -kv[1][1]):
             k = {"launches": cnt, "total_ms": round(ms, 3), "share": round(ms / tot_ms, 4) if tot_ms else None}
             if name in KERNEL_BYTES_PER_PX and ms > 0:
-                frames_factor = (P + 1) if name == "polyexp_tiled" else P
+                frames_factor = (P + 1) if name.startswith("polyexp") else P
                 byts = KERNEL_BYTES_PER_PX[name] * px_per_launch_total[name] * frames_factor
                 k["achieved_gbs"] = round(byts / (ms * 1e-3) / 1e9, 1)
                 k["alg_bytes_per_launch"] = round(byts / cnt, 1)
@@ -350,6 +357,8 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--ref-pairs-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="pairs per launch inside a shot (0 = engine default)")
+    ap.add_argument("--batch-scale0", type=int, default=-1, help="pairs per launch at scale 0 (-1 = default, 0 = same as --batch)")
     args = ap.parse_args()
 
     from optical_flow_b200 import dist

@@ -46,6 +46,9 @@ k_box_v_generic(Planes5 M, int W, int H, int m, double* __restrict__ tmp, size_t
     const float* p = M.ch(c);
     double s = 0;
     for (int i = -m; i <= m; i++) s += (double)p[(size_t)min(max(y + i, 0), H - 1) * M.pitch + x];
+    // winsize == 1: cv2 seeds its running sum with row0*(m+2) and then adds row[y+m]-row[y-m-1]; for
+    // m == 0 that telescopes to M[y] + M[0], not M[y] (a quirk to reproduce).
+    if (m == 0) s += (double)p[x];
     tmp[(size_t)c * tplane + (size_t)y * tpitch + x] = s;
 }
 
@@ -60,6 +63,7 @@ k_box_h_solve_generic(const double* __restrict__ tmp, size_t tplane, int tpitch,
         const double* row = tmp + (size_t)c * tplane + (size_t)y * tpitch;
         double s = 0;
         for (int i = -m; i <= m; i++) s += row[min(max(x + i, 0), W - 1)];
+        if (m == 0) s += row[0];          // same quirk horizontally: vsum[x] + vsum[0]
         b[c] = s * scale;
     }
     flow[(size_t)y * W + x] = solve_flow(b[0], b[1], b[2], b[3], b[4]);
@@ -103,7 +107,6 @@ k_gauss_h_solve_generic(const float* __restrict__ tmp, size_t tplane, int tpitch
 // k_box_strip<M>
 // ------------------------------------------------------------------------------------------------
 constexpr int BS_CW = 96;              // columns loaded per CTA (3 warps per channel)
-constexpr int BS_CWW = BS_CW / 32;
 constexpr int BS_THREADS = 5 * BS_CW;  // 480
 constexpr int BS_VPITCH = BS_CW + 1;   // odd pitch: H-phase lanes walk rows, keep them on distinct banks
 

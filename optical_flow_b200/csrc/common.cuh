@@ -23,6 +23,58 @@ struct Planes5 {          // five planar f32 images
     __host__ __device__ float* ch(int c) const { return base + (size_t)c * plane; }
 };
 
+// Batched views: R planes of one pyramid level for a ring of frame slots; pair z of a batch reads the
+// slots (slot0+z) % nslots and (slot0+z+1) % nslots.
+struct SlotRing {
+    float* base;                // slot s at base + s * slot_stride
+    size_t slot_stride;         // floats
+    size_t plane;               // floats between the 5 planes of a slot
+    int pitch;
+    int nslots;
+    __host__ __device__ Planes5 slot(int s) const { return Planes5{base + (size_t)s * slot_stride, plane, pitch}; }
+};
+
+// first UpdateMatrices of a scale (iter.cu k_um0); batch item z
+struct Um0Args {
+    const float2* flow; size_t flow_item;   // SRC 1: flow of this scale; SRC 2: coarser flow (Wp x Hp); per-item stride in float2
+    int Wp, Hp; double sx_scale, sy_scale; float mul;
+    SlotRing R; int slot0;
+    float* M; size_t m_item, plane; int pitch;
+    int W, H;
+};
+
+// blur + solve (+ UpdateMatrices) (iter.cu k_iter); batch item z
+struct IterArgs {
+    const float* Min; float* Mout; size_t m_item, plane; int pitch;
+    SlotRing R; int slot0;
+    float2* flow; size_t flow_item;
+    int W, H, strip_rows; float c;          // c = 1e-3 * winsize^4
+};
+
+// polynomial expansion (polyexp.cu); batch item z = frame
+struct PolyArgs {
+    const void* src; size_t src_item;       // bytes between batch items
+    size_t src_pitch;                       // bytes between rows
+    int W, H;
+    SlotRing R; int slot0;                  // output slot (slot0 + z) % nslots
+    float g[9], xg[9], xxg[9];              // taps k = 0..n (f32, as cv2 builds them)
+    double gd[9], xgd[9], xxgd[9];          // the same values widened (exact)
+    double ig11, ig03, ig33, ig55;
+    int n;
+};
+
+// level image of scale k >= 1 (pyramid.cu, batched); T is the row-pass intermediate (H x Wk), I the result
+struct PyrArgs {
+    const void* src; size_t src_item, src_pitch;    // frames: bytes between batch items / rows
+    int W, H, Wk, Hk, ksize;
+    const float* taps;
+    const int* sx; const float* ax;                 // per destination column: source index, weight of the next one
+    const int* sy; const float* ay;                 // per destination row
+    float* T; size_t t_item;                        // floats
+    float* I; size_t i_item;
+    int pitch;                                      // row pitch of T and I (floats)
+};
+
 static inline int divup(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return divup(a, b) * b; }
 
@@ -60,10 +112,16 @@ void launch_pyr_h(Launch& L, const void* frame, int dtype, int W, int H, size_t 
 void launch_pyr_v(Launch& L, const float* T, int H, int t_pitch, const float* taps, int ksize,
                   float* I, int Wk, int Hk, int i_pitch);
 
+void launch_pyr2(Launch& L, int dtype, const PyrArgs& a, int batch);
+
 // polyexp.cu -- A.5/A.6
 struct PolyConst { const float* g; const float* xg; const float* xxg; int n; double ig11, ig03, ig33, ig55; };
 void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const PolyConst& pc,
                     float* tmp3 /* 3 planes */, Planes5 R, bool generic);
+// batched, unrolled variant: src_kind 0 = level image (f32), 1 = u8 frame + fused [1/4 1/2 1/4]^2 pre-blur
+// (scale 0), 2 = f32 frame + the same pre-blur.  Returns false when poly_n has no unrolled instance.
+bool polyexp2_supported(int n);
+void launch_polyexp2(Launch& L, int src_kind, const PolyArgs& a, int batch);
 
 // matrices.cu -- A.2 and A.8
 void launch_upsample_flow(Launch& L, const float2* prev, int Wp, int Hp, float2* flow, int W, int H, float mul);
@@ -73,6 +131,11 @@ void launch_update_matrices(Launch& L, Planes5 R0, Planes5 R1, const float2* flo
 void launch_interleave5(Launch& L, Planes5 src, int W, int H, float* dst /* (H,W,5) */);
 void launch_deinterleave5(Launch& L, const float* src /* (H,W,5) */, int W, int H, Planes5 dst);
 
+// iter.cu -- A.8 / A.9 / A.11 batched
+void launch_um0(Launch& L, int src, const Um0Args& a, int batch);
+bool iter_supported(int winsize);
+void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count);
+
 // blur_solve.cu -- A.9 / A.10
 void set_sm_count(int n);
 void launch_blur_solve_box(Launch& L, Planes5 M, int W, int H, int winsize, double* tmp /* 5 planes f64 */,
@@ -81,6 +144,11 @@ void launch_blur_solve_gauss(Launch& L, Planes5 M, int W, int H, int winsize, co
                              float* tmp /* 5 planes f32 */, float2* flow, bool generic);
 
 // viz.cu -- Appendix B
+// batched over pairs: flow / bgr / minmax / sums advance by *_item per batch element
+void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax /* 2 per item */,
+                          uint8_t* bgr, size_t bgr_item, int batch);
+void launch_sum_magnitude_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, double* acc /* 1 per item */,
+                                float* out /* 1 per item */, int batch);
 void launch_minmax_mag(Launch& L, const float2* flow, size_t n, unsigned* minmax /* [2], pre-set */);
 void launch_minmax_reset(Launch& L, unsigned* minmax);
 void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned* minmax, uint8_t* bgr);

@@ -7,12 +7,23 @@
 //     R[i]     = polyexp(level_image(frame_i, k))           i = 0, 1
 //     M        = UpdateMatrices(R0, R1, flow_k)
 //     repeat iterations:  flow_k = solve(blur(M));  M = UpdateMatrices(...) unless last
-// The per-frame part (level images + polynomial expansion, every scale) is kept in one of two
-// "frame slots", so that inside a shot each frame is expanded once and used by both of its pairs.
+//
+// B200-first re-organisation:
+//   * per-frame work (level images + polynomial expansion, every scale) is computed ONCE per frame into a
+//     ring of frame slots and shared by the two pairs the frame belongs to;
+//   * pairs of a shot are independent, so a CHUNK of `batch` pairs is processed per launch (blockIdx.z):
+//     the coarse scales (a few CTAs per pair) fill the 148 SMs and launch latency is amortised;
+//   * middle iterations run as ONE kernel (blur -> solve -> UpdateMatrices), M ping-pongs between two
+//     buffers, the flow of a middle iteration never reaches memory, and the first UpdateMatrices of a
+//     scale does the inter-scale up-sample on the fly (k_um0, k_iter in iter.cu);
+//   * scale 0's pre-blur is fused into the polynomial expansion (k_polyexp2 SRC 1/2).
+// Anything outside the fast paths (Gaussian window, winsize > 33, poly_n other than 3/5/7, iterations == 0,
+// option "generic_kernels") runs the simple per-item global-memory kernels with identical results.
 #include "common.cuh"
 #include "launch.cuh"
 #include "../../include/optflow_b200.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -29,32 +40,40 @@ thread_local std::string g_error;
 struct Level {
     int k = 0, W = 0, H = 0, pitch = 0, ksize = 0;
     double sigma = 0, scale = 1;
-    float* taps = nullptr;          // device, ksize floats
-    float* R[2] = {nullptr, nullptr};   // 5 planes each, per frame slot
-    float2* flow = nullptr;         // tight (H, W) float2; null at k == 0 (caller's buffer is used)
+    float* taps = nullptr;              // device, ksize floats
+    int* sx = nullptr; float* ax = nullptr;     // bilinear tables (k >= 1)
+    int* sy = nullptr; float* ay = nullptr;
+    float* R = nullptr;                 // ring of nslots x 5 planes
+    float2* flow = nullptr;             // batch x (H, W) float2 (k >= 1)
     size_t plane() const { return (size_t)H * pitch; }
+    size_t slot_stride() const { return 5 * plane(); }
+    size_t flow_item() const { return (size_t)W * H; }
 };
 
 struct Plan {
     bool valid = false;
-    int W = 0, H = 0, dtype = 0;
+    int W = 0, H = 0, dtype = 0, batch = 1, nslots = 2;
     ofb_params p{};
-    std::vector<Level> lv;          // index = k (0 = full resolution)
+    std::vector<Level> lv;              // index = k (0 = full resolution)
     int K = 0;
-    // scratch sized for scale 0
-    float* T = nullptr;             // H x pitch0   (horizontal pyramid pass)
-    float* I = nullptr;             // H0 x pitch0  (level image)
-    float* tmp3 = nullptr;          // 3 planes     (generic polyexp)
-    float* M = nullptr;             // 5 planes
-    double* btmp = nullptr;         // 5 planes f64 (generic blur; reused as f32 by the Gaussian path)
-    float* poly = nullptr;          // g, xg, xxg : 3 * (2n+1)
-    float* gtaps = nullptr;         // half taps of the Gaussian window, m+1
+    float* T = nullptr; size_t t_item = 0;      // batch x (H x pitch_1): row-pass intermediate of the pyramid
+    float* I = nullptr; size_t i_item = 0;      // batch x level image
+    float* tmp3 = nullptr;              // 3 planes (generic polyexp, one item)
+    float* M[2] = {nullptr, nullptr};   // batch x 5 planes, ping-pong
+    size_t m_item = 0;
+    double* btmp = nullptr;             // 5 planes f64 (generic blur, one item)
+    float* poly = nullptr;              // g, xg, xxg : 3 * (2n+1)
+    float* gtaps = nullptr;             // half taps of the Gaussian window, m+1
     PolyConst pc{};
-    void* frame[2] = {nullptr, nullptr};    // device copies of the two frames (tight rows)
-    float2* flow0 = nullptr;        // scale-0 flow when the caller keeps it on the device side of the host API
-    float2* flow0b = nullptr;       // second one for shots that download the flow
-    uint8_t* bgr[2] = {nullptr, nullptr};
+    PolyArgs pa{};                      // constants part filled once
+    uint8_t* f0 = nullptr;              // device copy of a single frame (first frame of a shot / `prev`)
+    uint8_t* fstage[2] = {nullptr, nullptr};    // 2 x batch frames (host shots)
+    float2* flow0[2] = {nullptr, nullptr};      // 2 x batch scale-0 flows
+    uint8_t* bgr[2] = {nullptr, nullptr};       // 2 x batch pictures
+    float* sums = nullptr;              // per-pair magnitude sums of a shot (host API), grown on demand
+    size_t sums_cap = 0;
     std::vector<void*> allocs;
+    bool fast_poly = false, fast_iter = false;
 };
 
 }  // namespace
@@ -67,15 +86,19 @@ struct ofb_context {
     std::string err;
     Profiler prof;
     bool generic = false;
+    int batch = 4;                      // pairs per launch inside a shot
+    int batch0 = 0;                     // pairs per launch at scale 0 (0 = same as batch)
     Plan plan;
-    unsigned* minmax = nullptr;     // [2]
-    double* sumacc = nullptr;       // [1]
-    float* sumout = nullptr;        // [1] device staging of one magnitude sum
-    float* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // scratch for stage / companion entry points
+    unsigned* minmax = nullptr;         // 2 per batch item
+    double* sumacc = nullptr;           // 1 per batch item
+    float* sumout = nullptr;            // device staging of magnitude sums (batch items)
+    float* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
+
+constexpr int MAX_BATCH = 64;
 
 int fail(ofb_context* c, int code, const std::string& msg)
 {
@@ -158,6 +181,19 @@ void poly_constants(int n, double sigma, std::vector<float>& tab, double ig[4])
     ig[0] = 1.0 / G11; ig[1] = -b / den; ig[2] = (a * c - b * b) / ((c - d) * den); ig[3] = 1.0 / G55;
 }
 
+void fill_poly_args(PolyArgs& pa, int n, const std::vector<float>& tab, const double ig[4])
+{
+    memset(&pa, 0, sizeof(pa));
+    pa.n = n;
+    int len = 2 * n + 1;
+    if (n <= 8)
+        for (int k = 0; k <= n; k++) {
+            pa.g[k] = tab[n + k]; pa.xg[k] = tab[len + n + k]; pa.xxg[k] = tab[2 * len + n + k];
+            pa.gd[k] = pa.g[k]; pa.xgd[k] = pa.xg[k]; pa.xxgd[k] = pa.xxg[k];
+        }
+    pa.ig11 = ig[0]; pa.ig03 = ig[1]; pa.ig33 = ig[2]; pa.ig55 = ig[3];
+}
+
 void gauss_half_taps(int winsize, std::vector<float>& k)
 {
     int m = winsize / 2;
@@ -167,6 +203,21 @@ void gauss_half_taps(int winsize, std::vector<float>& k)
     for (int i = 1; i <= m; i++) { float t = (float)std::exp(-i * i / (2 * sigma * sigma)); k[i] = t; s += t * 2; }
     s = 1. / s;
     for (int i = 0; i <= m; i++) k[i] = (float)(k[i] * s);
+}
+
+// cv::resize(INTER_LINEAR) coordinate rule, double-precision coordinates
+void linear_table(int dst, int src, std::vector<int>& idx, std::vector<float>& w1)
+{
+    idx.resize(dst); w1.resize(dst);
+    double scale = 1.0 / ((double)dst / src);
+    for (int d = 0; d < dst; d++) {
+        double f = (d + 0.5) * scale - 0.5;
+        int s = (int)std::floor(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0; }
+        if (s >= src - 1) { s = src - 1; f = 0; }
+        idx[d] = s; w1[d] = (float)f;
+    }
 }
 
 // ---- plan -----------------------------------------------------------------------------------
@@ -182,6 +233,13 @@ template <class T> int dalloc(ofb_context* ctx, Plan& pl, T** out, size_t count)
     CU(cudaMalloc(&p, count * sizeof(T) + 256));
     pl.allocs.push_back(p);
     *out = (T*)p;
+    return 0;
+}
+
+template <class T> int dupload(ofb_context* ctx, Plan& pl, T** out, const std::vector<T>& v)
+{
+    if (int rc = dalloc(ctx, pl, out, std::max<size_t>(v.size(), 1))) return rc;
+    CU(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -206,17 +264,19 @@ int validate(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p)
     return 0;
 }
 
-int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p)
+int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, int batch)
 {
     Plan& pl = ctx->plan;
-    if (pl.valid && pl.W == W && pl.H == H && pl.dtype == dtype && same_params(pl.p, *p)) return 0;
+    batch = std::max(1, std::min(batch, MAX_BATCH));
+    if (pl.valid && pl.W == W && pl.H == H && pl.dtype == dtype && same_params(pl.p, *p) && pl.batch >= batch) return 0;
     CU(cudaStreamSynchronize(ctx->s_compute));
     CU(cudaStreamSynchronize(ctx->s_h2d));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     free_plan(pl);
-    pl.W = W; pl.H = H; pl.dtype = dtype; pl.p = *p;
+    pl.W = W; pl.H = H; pl.dtype = dtype; pl.p = *p; pl.batch = batch; pl.nslots = batch + 1;
     pl.K = num_scales(W, H, p->pyr_scale, p->levels);
     pl.lv.resize(pl.K + 1);
+    const size_t B = (size_t)batch;
     for (int k = 0; k <= pl.K; k++) {
         Level& l = pl.lv[k];
         l.k = k;
@@ -225,96 +285,170 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p)
         l.pitch = round_up(l.W, 32);
         std::vector<float> taps;
         gaussian_taps(l.ksize, l.sigma, taps);
-        if (int rc = dalloc(ctx, pl, &l.taps, taps.size())) return rc;
-        CU(cudaMemcpy(l.taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
-        for (int s = 0; s < 2; s++)
-            if (int rc = dalloc(ctx, pl, &l.R[s], 5 * l.plane())) return rc;
+        if (int rc = dupload(ctx, pl, &l.taps, taps)) return rc;
+        std::vector<int> ix, iy; std::vector<float> wx, wy;
+        linear_table(l.W, W, ix, wx);
+        linear_table(l.H, H, iy, wy);
+        if (int rc = dupload(ctx, pl, &l.sx, ix)) return rc;
+        if (int rc = dupload(ctx, pl, &l.ax, wx)) return rc;
+        if (int rc = dupload(ctx, pl, &l.sy, iy)) return rc;
+        if (int rc = dupload(ctx, pl, &l.ay, wy)) return rc;
+        if (int rc = dalloc(ctx, pl, &l.R, (size_t)pl.nslots * l.slot_stride())) return rc;
         if (k > 0)
-            if (int rc = dalloc(ctx, pl, &l.flow, (size_t)l.W * l.H)) return rc;
+            if (int rc = dalloc(ctx, pl, &l.flow, B * l.flow_item())) return rc;
     }
     const Level& l0 = pl.lv[0];
-    size_t plane0 = l0.plane();
-    if (int rc = dalloc(ctx, pl, &pl.T, (size_t)H * l0.pitch)) return rc;
-    if (int rc = dalloc(ctx, pl, &pl.I, plane0)) return rc;
+    const size_t plane0 = l0.plane();
+    pl.t_item = (size_t)H * l0.pitch;
+    pl.i_item = plane0;
+    pl.m_item = 5 * plane0;
+    if (int rc = dalloc(ctx, pl, &pl.T, B * pl.t_item)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.I, B * pl.i_item)) return rc;
     if (int rc = dalloc(ctx, pl, &pl.tmp3, 3 * plane0)) return rc;
-    if (int rc = dalloc(ctx, pl, &pl.M, 5 * plane0)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.M[0], B * pl.m_item)) return rc;
+    if (int rc = dalloc(ctx, pl, &pl.M[1], B * pl.m_item)) return rc;
     if (int rc = dalloc(ctx, pl, &pl.btmp, 5 * plane0)) return rc;
     std::vector<float> tab; double ig[4];
     poly_constants(p->poly_n, p->poly_sigma, tab, ig);
-    if (int rc = dalloc(ctx, pl, &pl.poly, tab.size())) return rc;
-    CU(cudaMemcpy(pl.poly, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (int rc = dupload(ctx, pl, &pl.poly, tab)) return rc;
     int len = 2 * p->poly_n + 1;
     pl.pc = PolyConst{pl.poly, pl.poly + len, pl.poly + 2 * len, p->poly_n, ig[0], ig[1], ig[2], ig[3]};
+    fill_poly_args(pl.pa, p->poly_n, tab, ig);
     std::vector<float> gk;
     gauss_half_taps(p->winsize, gk);
-    if (int rc = dalloc(ctx, pl, &pl.gtaps, gk.size())) return rc;
-    CU(cudaMemcpy(pl.gtaps, gk.data(), gk.size() * sizeof(float), cudaMemcpyHostToDevice));
-    size_t esz = dtype == OFB_U8 ? 1 : 4;
+    if (int rc = dupload(ctx, pl, &pl.gtaps, gk)) return rc;
+    const size_t esz = dtype == OFB_U8 ? 1 : 4, n = (size_t)W * H;
+    if (int rc = dalloc(ctx, pl, &pl.f0, n * esz)) return rc;
     for (int s = 0; s < 2; s++) {
-        uint8_t* f = nullptr;
-        if (int rc = dalloc(ctx, pl, &f, (size_t)W * H * esz)) return rc;
-        pl.frame[s] = f;
-        if (int rc = dalloc(ctx, pl, &pl.bgr[s], (size_t)W * H * 3)) return rc;
+        if (int rc = dalloc(ctx, pl, &pl.fstage[s], B * n * esz)) return rc;
+        if (int rc = dalloc(ctx, pl, &pl.flow0[s], B * n)) return rc;
+        if (int rc = dalloc(ctx, pl, &pl.bgr[s], B * n * 3)) return rc;
     }
-    if (int rc = dalloc(ctx, pl, &pl.flow0, (size_t)W * H)) return rc;
-    if (int rc = dalloc(ctx, pl, &pl.flow0b, (size_t)W * H)) return rc;
+    pl.fast_poly = polyexp2_supported(p->poly_n);
+    pl.fast_iter = !(p->flags & OFB_OPTFLOW_FARNEBACK_GAUSSIAN) && iter_supported(p->winsize) && p->iterations >= 1;
     pl.valid = true;
     return 0;
 }
 
-Planes5 planes(float* base, const Level& l) { return Planes5{base, l.plane(), l.pitch}; }
+Planes5 slot_planes(const Level& l, int slot) { return Planes5{l.R + (size_t)slot * l.slot_stride(), l.plane(), l.pitch}; }
+SlotRing ring(const Plan& pl, const Level& l) { return SlotRing{l.R, l.slot_stride(), l.plane(), l.pitch, pl.nslots}; }
+Planes5 m_planes(const Plan& pl, const Level& l, int which, int item)
+{
+    return Planes5{pl.M[which] + (size_t)item * pl.m_item, l.plane(), l.pitch};
+}
 
-// Per-frame part: level images + polynomial expansion for every scale, into frame slot `slot`.
-void expand_frame(ofb_context* ctx, Launch& L, const void* d_frame, size_t pitch_bytes, int slot)
+// Per-frame part for `count` consecutive frames (first one = frame index f0 of the shot -> slot f0 % nslots).
+// Frames are `item_bytes` apart starting at d_frames, rows `pitch_bytes` apart.
+void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t item_bytes, size_t pitch_bytes, int f0, int count)
 {
     Plan& pl = ctx->plan;
+    const bool fast = pl.fast_poly && !ctx->generic;
     for (int k = pl.K; k >= 0; k--) {
         Level& l = pl.lv[k];
-        launch_pyr_h(L, d_frame, pl.dtype, pl.W, pl.H, pitch_bytes, l.taps, l.ksize, pl.T, l.W, l.pitch);
-        launch_pyr_v(L, pl.T, pl.H, l.pitch, l.taps, l.ksize, pl.I, l.W, l.H, l.pitch);
-        launch_polyexp(L, pl.I, l.W, l.H, l.pitch, pl.pc, pl.tmp3, planes(l.R[slot], l), ctx->generic);
+        const int slot0 = f0 % pl.nslots;
+        if (fast && k == 0) {
+            PolyArgs a = pl.pa;
+            a.src = d_frames; a.src_item = item_bytes; a.src_pitch = pitch_bytes;
+            a.W = l.W; a.H = l.H; a.R = ring(pl, l); a.slot0 = slot0;
+            launch_polyexp2(L, pl.dtype == OFB_U8 ? 1 : 2, a, count);
+            continue;
+        }
+        if (fast) {
+            PyrArgs py{};
+            py.src = d_frames; py.src_item = item_bytes; py.src_pitch = pitch_bytes;
+            py.W = pl.W; py.H = pl.H; py.Wk = l.W; py.Hk = l.H; py.ksize = l.ksize; py.taps = l.taps;
+            py.sx = l.sx; py.ax = l.ax; py.sy = l.sy; py.ay = l.ay;
+            py.T = pl.T; py.t_item = pl.t_item; py.I = pl.I; py.i_item = pl.i_item; py.pitch = l.pitch;
+            launch_pyr2(L, pl.dtype, py, count);
+            PolyArgs a = pl.pa;
+            a.src = pl.I; a.src_item = pl.i_item * sizeof(float); a.src_pitch = (size_t)l.pitch * sizeof(float);
+            a.W = l.W; a.H = l.H; a.R = ring(pl, l); a.slot0 = slot0;
+            launch_polyexp2(L, 0, a, count);
+            continue;
+        }
+        for (int z = 0; z < count; z++) {
+            const char* fr = (const char*)d_frames + (size_t)z * item_bytes;
+            launch_pyr_h(L, fr, pl.dtype, pl.W, pl.H, pitch_bytes, l.taps, l.ksize, pl.T, l.W, l.pitch);
+            launch_pyr_v(L, pl.T, pl.H, l.pitch, l.taps, l.ksize, pl.I, l.W, l.H, l.pitch);
+            launch_polyexp(L, pl.I, l.W, l.H, l.pitch, pl.pc, pl.tmp3, slot_planes(l, (f0 + z) % pl.nslots), ctx->generic);
+        }
     }
 }
 
-// Per-pair part: coarse-to-fine iterations; d_flow is the (H, W) float2 output (read first when
-// OPTFLOW_USE_INITIAL_FLOW).
-void solve_pair(ofb_context* ctx, Launch& L, int slot0, int slot1, float2* d_flow)
+// Per-pair part for `count` consecutive pairs; pair z uses the slots of frames t0+z and t0+z+1 and writes
+// its scale-0 flow to d_flow + z * flow_item (float2 units).  `initial` = OPTFLOW_USE_INITIAL_FLOW (count == 1).
+void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow, size_t flow_item)
 {
     Plan& pl = ctx->plan;
     const ofb_params& p = pl.p;
     const bool gaussian = (p.flags & OFB_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
+    const bool initial = (p.flags & OFB_OPTFLOW_USE_INITIAL_FLOW) != 0;
+    const bool fast = pl.fast_iter && !ctx->generic;
+    const float c4 = (float)(1e-3 * (double)p.winsize * p.winsize * p.winsize * p.winsize);
+    const float up_mul = (float)(1. / p.pyr_scale);
     for (int k = pl.K; k >= 0; k--) {
         Level& l = pl.lv[k];
         float2* flow = k == 0 ? d_flow : l.flow;
-        if (k == pl.K) {
-            if (p.flags & OFB_OPTFLOW_USE_INITIAL_FLOW) {
-                if (k > 0) launch_area_flow(L, d_flow, pl.W, pl.H, flow, l.W, l.H, (float)l.scale);
-                // k == 0: same-size INTER_AREA is a copy and scale == 1: the buffer already holds it
-            } else {
-                cudaMemsetAsync(flow, 0, sizeof(float2) * (size_t)l.W * l.H, L.stream);
+        const size_t fitem = k == 0 ? flow_item : l.flow_item();
+        const int slot0 = t0 % pl.nslots;
+        if (k == pl.K && initial && k > 0)
+            launch_area_flow(L, d_flow, pl.W, pl.H, flow, l.W, l.H, (float)l.scale);   // count == 1
+        if (fast) {
+            const int sub = (k == 0 && ctx->batch0 > 0) ? std::min(ctx->batch0, count) : count;
+            for (int z0 = 0; z0 < count; z0 += sub) {
+                const int nb = std::min(sub, count - z0);
+                Um0Args u{};
+                u.R = ring(pl, l); u.slot0 = (slot0 + z0) % pl.nslots;
+                u.M = pl.M[0] + (size_t)z0 * pl.m_item; u.m_item = pl.m_item; u.plane = l.plane(); u.pitch = l.pitch;
+                u.W = l.W; u.H = l.H;
+                int src = 0;
+                if (k == pl.K) {
+                    if (initial) { src = 1; u.flow = flow + (size_t)z0 * fitem; u.flow_item = fitem; }
+                } else {
+                    const Level& cl = pl.lv[k + 1];
+                    src = 2;
+                    u.flow = cl.flow + (size_t)z0 * cl.flow_item(); u.flow_item = cl.flow_item();
+                    u.Wp = cl.W; u.Hp = cl.H;
+                    u.sx_scale = 1.0 / ((double)l.W / cl.W); u.sy_scale = 1.0 / ((double)l.H / cl.H);
+                    u.mul = up_mul;
+                }
+                launch_um0(L, src, u, nb);
+                int cur = 0;
+                for (int i = 0; i < p.iterations; i++) {
+                    const bool last = i == p.iterations - 1;
+                    IterArgs a{};
+                    a.Min = pl.M[cur] + (size_t)z0 * pl.m_item; a.Mout = pl.M[cur ^ 1] + (size_t)z0 * pl.m_item;
+                    a.m_item = pl.m_item; a.plane = l.plane(); a.pitch = l.pitch;
+                    a.R = ring(pl, l); a.slot0 = (slot0 + z0) % pl.nslots;
+                    a.flow = flow + (size_t)z0 * fitem; a.flow_item = fitem;
+                    a.W = l.W; a.H = l.H; a.c = c4;
+                    launch_iter(L, a, p.winsize, !last, nb, ctx->sm_count);
+                    cur ^= 1;
+                }
             }
-        } else {
-            const Level& c = pl.lv[k + 1];
-            launch_upsample_flow(L, c.flow, c.W, c.H, flow, l.W, l.H, (float)(1. / p.pyr_scale));
+            continue;
         }
-        Planes5 R0 = planes(l.R[slot0], l), R1 = planes(l.R[slot1], l), M = planes(pl.M, l);
-        launch_update_matrices(L, R0, R1, flow, l.W, l.H, M);
-        for (int i = 0; i < p.iterations; i++) {
-            if (gaussian)
-                launch_blur_solve_gauss(L, M, l.W, l.H, p.winsize, pl.gtaps, (float*)pl.btmp, flow, ctx->generic);
-            else
-                launch_blur_solve_box(L, M, l.W, l.H, p.winsize, pl.btmp, flow, ctx->generic);
-            if (i < p.iterations - 1) launch_update_matrices(L, R0, R1, flow, l.W, l.H, M);
+        // generic path: explicit flow buffers, one item at a time
+        for (int z = 0; z < count; z++) {
+            float2* fl = flow + (size_t)z * fitem;
+            if (k == pl.K) {
+                if (!initial) cudaMemsetAsync(fl, 0, sizeof(float2) * l.flow_item(), L.stream);
+            } else {
+                const Level& cl = pl.lv[k + 1];
+                launch_upsample_flow(L, cl.flow + (size_t)z * cl.flow_item(), cl.W, cl.H, fl, l.W, l.H, up_mul);
+            }
+            Planes5 R0 = slot_planes(l, (slot0 + z) % pl.nslots), R1 = slot_planes(l, (slot0 + z + 1) % pl.nslots);
+            Planes5 M = m_planes(pl, l, 0, 0);
+            launch_update_matrices(L, R0, R1, fl, l.W, l.H, M);
+            for (int i = 0; i < p.iterations; i++) {
+                if (gaussian) launch_blur_solve_gauss(L, M, l.W, l.H, p.winsize, pl.gtaps, (float*)pl.btmp, fl, true);
+                else launch_blur_solve_box(L, M, l.W, l.H, p.winsize, pl.btmp, fl, true);
+                if (i < p.iterations - 1) launch_update_matrices(L, R0, R1, fl, l.W, l.H, M);
+            }
         }
     }
 }
 
-void picture(ofb_context* ctx, Launch& L, const float2* d_flow, size_t n, uint8_t* d_bgr)
-{
-    launch_minmax_reset(L, ctx->minmax);
-    launch_minmax_mag(L, d_flow, n, ctx->minmax);
-    launch_flow_to_bgr(L, d_flow, n, ctx->minmax, d_bgr);
-}
 
 int stage_buf(ofb_context* ctx, int i, size_t bytes, float** out)
 {
@@ -334,6 +468,18 @@ int upload_frame(ofb_context* ctx, const void* src, size_t pitch, int W, int H, 
     if (pitch == 0) pitch = row;
     if (pitch < row) return fail(ctx, OFB_ERR_BAD_ARG, "row pitch smaller than a row");
     CU(cudaMemcpy2DAsync(dst, row, src, pitch, row, H, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+void picture(ofb_context* ctx, Launch& L, const float2* d_flow, size_t flow_item, size_t n, uint8_t* d_bgr, size_t bgr_item, int count)
+{
+    launch_picture_batch(L, d_flow, flow_item, n, ctx->minmax, d_bgr, bgr_item, count);
+}
+
+int no_initial_flow(ofb_context* ctx, const ofb_params* p)
+{
+    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
+        return fail(ctx, OFB_ERR_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is only meaningful through ofb_farneback_*");
     return 0;
 }
 
@@ -391,9 +537,9 @@ int ofb_create(int device, ofb_context** out)
     }
     ok(cudaEventCreate(&c->ev_t0));
     ok(cudaEventCreate(&c->ev_t1));
-    ok(cudaMalloc((void**)&c->minmax, 256));
-    ok(cudaMalloc((void**)&c->sumacc, 256));
-    ok(cudaMalloc((void**)&c->sumout, 256));
+    ok(cudaMalloc((void**)&c->minmax, sizeof(unsigned) * 2 * MAX_BATCH + 256));
+    ok(cudaMalloc((void**)&c->sumacc, sizeof(double) * MAX_BATCH + 256));
+    ok(cudaMalloc((void**)&c->sumout, sizeof(float) * MAX_BATCH + 256));
     if (rc != cudaSuccess) {
         std::string m = std::string("context setup: ") + cudaGetErrorString(rc);
         delete c;
@@ -477,12 +623,12 @@ int ofb_farneback_device(ofb_context* ctx, const void* d_prev, const void* d_nex
     if (int rc = validate(ctx, W, H, dtype, p)) return rc;
     if (!d_prev || !d_next || !d_flow) return fail(ctx, OFB_ERR_BAD_ARG, "null frame or flow pointer");
     CU(cudaSetDevice(ctx->device));
-    if (int rc = ensure_plan(ctx, W, H, dtype, p)) return rc;
+    if (int rc = ensure_plan(ctx, W, H, dtype, p, 1)) return rc;
     size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4);
     Launch L{ctx->s_compute, &ctx->prof};
-    expand_frame(ctx, L, d_prev, prev_pitch ? prev_pitch : row, 0);
-    expand_frame(ctx, L, d_next, next_pitch ? next_pitch : row, 1);
-    solve_pair(ctx, L, 0, 1, (float2*)d_flow);
+    expand_frames(ctx, L, d_prev, 0, prev_pitch ? prev_pitch : row, 0, 1);
+    expand_frames(ctx, L, d_next, 0, next_pitch ? next_pitch : row, 1, 1);
+    solve_pairs(ctx, L, 0, 1, (float2*)d_flow, (size_t)W * H);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->s_compute));
     return OFB_OK;
@@ -494,20 +640,20 @@ int ofb_farneback_host(ofb_context* ctx, const void* prev, const void* next, int
     if (int rc = validate(ctx, W, H, dtype, p)) return rc;
     if (!prev || !next || !flow) return fail(ctx, OFB_ERR_BAD_ARG, "null frame or flow pointer");
     CU(cudaSetDevice(ctx->device));
-    if (int rc = ensure_plan(ctx, W, H, dtype, p)) return rc;
+    if (int rc = ensure_plan(ctx, W, H, dtype, p, 1)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t s = ctx->s_compute;
-    if (int rc = upload_frame(ctx, prev, prev_pitch, W, H, dtype, pl.frame[0], s)) return rc;
-    if (int rc = upload_frame(ctx, next, next_pitch, W, H, dtype, pl.frame[1], s)) return rc;
+    if (int rc = upload_frame(ctx, prev, prev_pitch, W, H, dtype, pl.f0, s)) return rc;
+    if (int rc = upload_frame(ctx, next, next_pitch, W, H, dtype, pl.fstage[0], s)) return rc;
     size_t fbytes = sizeof(float2) * (size_t)W * H;
-    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) CU(cudaMemcpyAsync(pl.flow0, flow, fbytes, cudaMemcpyHostToDevice, s));
+    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) CU(cudaMemcpyAsync(pl.flow0[0], flow, fbytes, cudaMemcpyHostToDevice, s));
     size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4);
     Launch L{s, &ctx->prof};
-    expand_frame(ctx, L, pl.frame[0], row, 0);
-    expand_frame(ctx, L, pl.frame[1], row, 1);
-    solve_pair(ctx, L, 0, 1, pl.flow0);
+    expand_frames(ctx, L, pl.f0, 0, row, 0, 1);
+    expand_frames(ctx, L, pl.fstage[0], 0, row, 1, 1);
+    solve_pairs(ctx, L, 0, 1, pl.flow0[0], (size_t)W * H);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(flow, pl.flow0, fbytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(flow, pl.flow0[0], fbytes, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return OFB_OK;
 }
@@ -518,7 +664,7 @@ int ofb_flow_to_bgr_device(ofb_context* ctx, const float* d_flow, int W, int H, 
     if (!ctx || !d_flow || !d_bgr || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     Launch L{ctx->s_compute, &ctx->prof};
-    picture(ctx, L, (const float2*)d_flow, (size_t)W * H, d_bgr);
+    picture(ctx, L, (const float2*)d_flow, 0, (size_t)W * H, d_bgr, 0, 1);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->s_compute));
     return OFB_OK;
@@ -535,7 +681,7 @@ int ofb_flow_to_bgr_host(ofb_context* ctx, const float* flow, int W, int H, uint
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
     Launch L{s, &ctx->prof};
-    picture(ctx, L, (const float2*)df, n, (uint8_t*)db);
+    picture(ctx, L, (const float2*)df, 0, n, (uint8_t*)db, 0, 1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(bgr, db, n * 3, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -547,7 +693,7 @@ int ofb_sum_magnitude_device(ofb_context* ctx, const float* d_flow, int W, int H
     if (!ctx || !d_flow || !d_out || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     Launch L{ctx->s_compute, &ctx->prof};
-    launch_sum_magnitude(L, (const float2*)d_flow, (size_t)W * H, ctx->sumacc, d_out);
+    launch_sum_magnitude_batch(L, (const float2*)d_flow, 0, (size_t)W * H, ctx->sumacc, d_out, 1);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->s_compute));
     return OFB_OK;
@@ -563,7 +709,7 @@ int ofb_sum_magnitude_host(ofb_context* ctx, const float* flow, int W, int H, fl
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
     Launch L{s, &ctx->prof};
-    launch_sum_magnitude(L, (const float2*)df, n, ctx->sumacc, ctx->sumout);
+    launch_sum_magnitude_batch(L, (const float2*)df, 0, n, ctx->sumacc, ctx->sumout, 1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, ctx->sumout, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -596,25 +742,24 @@ int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtyp
 {
     if (int rc = validate(ctx, W, H, dtype, p)) return rc;
     if (!prev || !next) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer");
-    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
-        return fail(ctx, OFB_ERR_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is only meaningful through ofb_farneback_*");
+    if (int rc = no_initial_flow(ctx, p)) return rc;
     CU(cudaSetDevice(ctx->device));
-    if (int rc = ensure_plan(ctx, W, H, dtype, p)) return rc;
+    if (int rc = ensure_plan(ctx, W, H, dtype, p, 1)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t s = ctx->s_compute;
-    if (int rc = upload_frame(ctx, prev, 0, W, H, dtype, pl.frame[0], s)) return rc;
-    if (int rc = upload_frame(ctx, next, 0, W, H, dtype, pl.frame[1], s)) return rc;
+    if (int rc = upload_frame(ctx, prev, 0, W, H, dtype, pl.f0, s)) return rc;
+    if (int rc = upload_frame(ctx, next, 0, W, H, dtype, pl.fstage[0], s)) return rc;
     size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4), n = (size_t)W * H;
     Launch L{s, &ctx->prof};
-    expand_frame(ctx, L, pl.frame[0], row, 0);
-    expand_frame(ctx, L, pl.frame[1], row, 1);
-    solve_pair(ctx, L, 0, 1, pl.flow0);
-    if (bgr) picture(ctx, L, pl.flow0, n, pl.bgr[0]);
-    if (magsum) launch_sum_magnitude(L, pl.flow0, n, ctx->sumacc, ctx->sumout);
+    expand_frames(ctx, L, pl.f0, 0, row, 0, 1);
+    expand_frames(ctx, L, pl.fstage[0], 0, row, 1, 1);
+    solve_pairs(ctx, L, 0, 1, pl.flow0[0], n);
+    if (bgr) picture(ctx, L, pl.flow0[0], 0, n, pl.bgr[0], 0, 1);
+    if (magsum) launch_sum_magnitude_batch(L, pl.flow0[0], 0, n, ctx->sumacc, ctx->sumout, 1);
     CU(cudaGetLastError());
     if (bgr) CU(cudaMemcpyAsync(bgr, pl.bgr[0], n * 3, cudaMemcpyDeviceToHost, s));
     if (magsum) CU(cudaMemcpyAsync(magsum, ctx->sumout, 4, cudaMemcpyDeviceToHost, s));
-    if (flow) CU(cudaMemcpyAsync(flow, pl.flow0, n * 8, cudaMemcpyDeviceToHost, s));
+    if (flow) CU(cudaMemcpyAsync(flow, pl.flow0[0], n * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return OFB_OK;
 }
@@ -624,22 +769,23 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
 {
     if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
     if (!d_frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
-    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
-        return fail(ctx, OFB_ERR_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is only meaningful through ofb_farneback_*");
+    if (int rc = no_initial_flow(ctx, p)) return rc;
     CU(cudaSetDevice(ctx->device));
-    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p)) return rc;
+    const int B = std::max(1, std::min(ctx->batch, std::min(n_frames - 1, MAX_BATCH)));
+    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t s = ctx->s_compute;
-    size_t n = (size_t)W * H;
+    const size_t n = (size_t)W * H;
     Launch L{s, &ctx->prof};
     CU(cudaEventRecord(ctx->ev_t0, s));
-    expand_frame(ctx, L, d_frames, (size_t)W, 0);
-    for (int t = 0; t + 1 < n_frames; t++) {
-        expand_frame(ctx, L, d_frames + (size_t)(t + 1) * n, (size_t)W, (t + 1) & 1);
-        float2* fl = d_flow ? (float2*)d_flow + (size_t)t * n : pl.flow0;
-        solve_pair(ctx, L, t & 1, (t + 1) & 1, fl);
-        if (d_bgr) picture(ctx, L, fl, n, d_bgr + (size_t)t * n * 3);
-        if (d_magsum) launch_sum_magnitude(L, fl, n, ctx->sumacc, d_magsum + t);
+    expand_frames(ctx, L, d_frames, n, (size_t)W, 0, 1);
+    for (int t0 = 0; t0 + 1 < n_frames; t0 += B) {
+        const int b = std::min(B, n_frames - 1 - t0);
+        expand_frames(ctx, L, d_frames + (size_t)(t0 + 1) * n, n, (size_t)W, t0 + 1, b);
+        float2* fl = d_flow ? (float2*)d_flow + (size_t)t0 * n : pl.flow0[0];
+        solve_pairs(ctx, L, t0, b, fl, n);
+        if (d_bgr) picture(ctx, L, fl, n, n, d_bgr + (size_t)t0 * n * 3, n * 3, b);
+        if (d_magsum) launch_sum_magnitude_batch(L, fl, n, n, ctx->sumacc, d_magsum + t0, b);
     }
     CU(cudaEventRecord(ctx->ev_t1, s));
     CU(cudaGetLastError());
@@ -653,56 +799,50 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
 {
     if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
     if (!frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
-    if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
-        return fail(ctx, OFB_ERR_UNSUPPORTED, "OPTFLOW_USE_INITIAL_FLOW is only meaningful through ofb_farneback_*");
+    if (int rc = no_initial_flow(ctx, p)) return rc;
     CU(cudaSetDevice(ctx->device));
-    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p)) return rc;
+    const int B = std::max(1, std::min(ctx->batch, std::min(n_frames - 1, MAX_BATCH)));
+    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t sc = ctx->s_compute, su = ctx->s_h2d, sd = ctx->s_d2h;
     const size_t n = (size_t)W * H;
     float* d_sums = nullptr;
     if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)(n_frames - 1), &d_sums)) return rc;
     Launch L{sc, &ctx->prof};
-    float2* dflow[2] = {pl.flow0, pl.flow0b};
+    const int n_pairs = n_frames - 1;
+    const int n_chunks = (n_pairs + B - 1) / B;
 
     CU(cudaEventRecord(ctx->ev_t0, su));
-    // Uploads run ahead on s_h2d (double-buffered device frames), pictures / flows drain on s_d2h
-    // (double-buffered outputs); the compute stream only waits on the events it needs.
-    auto upload = [&](int j) -> int {
-        int b = j & 1;
-        if (j >= 2) CU(cudaStreamWaitEvent(su, ctx->ev_frame_free[b], 0));
-        CU(cudaMemcpyAsync(pl.frame[b], frames + (size_t)j * n, n, cudaMemcpyHostToDevice, su));
-        CU(cudaEventRecord(ctx->ev_h2d[b], su));
-        return 0;
-    };
-    auto expand = [&](int j) -> int {
-        int b = j & 1;
-        CU(cudaStreamWaitEvent(sc, ctx->ev_h2d[b], 0));
-        expand_frame(ctx, L, pl.frame[b], (size_t)W, b);
-        CU(cudaEventRecord(ctx->ev_frame_free[b], sc));
+    // Uploads run ahead on s_h2d (frames of chunk c go to fstage[c & 1]), results drain on s_d2h
+    // (pictures / flows of chunk c sit in bgr[c & 1] / flow0[c & 1]); the compute stream only waits on
+    // the events it needs, so H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c.
+    CU(cudaMemcpyAsync(pl.f0, frames, n, cudaMemcpyHostToDevice, su));
+    auto upload = [&](int c) -> int {
+        const int t0 = c * B, b = std::min(B, n_pairs - t0), par = c & 1;
+        if (c >= 2) CU(cudaStreamWaitEvent(su, ctx->ev_frame_free[par], 0));
+        CU(cudaMemcpyAsync(pl.fstage[par], frames + (size_t)(t0 + 1) * n, (size_t)b * n, cudaMemcpyHostToDevice, su));
+        CU(cudaEventRecord(ctx->ev_h2d[par], su));
         return 0;
     };
     if (int rc = upload(0)) return rc;
-    if (n_frames > 1) if (int rc = upload(1)) return rc;
-    if (int rc = expand(0)) return rc;
-    for (int t = 0; t + 1 < n_frames; t++) {
-        int b = t & 1;
-        if (int rc = expand(t + 1)) return rc;
-        if (t + 2 < n_frames) if (int rc = upload(t + 2)) return rc;
-        if (t >= 2) CU(cudaStreamWaitEvent(sc, ctx->ev_out_free[b], 0));
-        solve_pair(ctx, L, t & 1, (t + 1) & 1, dflow[b]);
-        if (bgr) picture(ctx, L, dflow[b], n, pl.bgr[b]);
-        if (magsum) launch_sum_magnitude(L, dflow[b], n, ctx->sumacc, d_sums + t);
-        CU(cudaEventRecord(ctx->ev_out_ready[b], sc));
-        CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[b], 0));
-        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t * n * 3, pl.bgr[b], n * 3, cudaMemcpyDeviceToHost, sd));
-        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t * n * 2, dflow[b], n * 8, cudaMemcpyDeviceToHost, sd));
-        CU(cudaEventRecord(ctx->ev_out_free[b], sd));
+    for (int c = 0; c < n_chunks; c++) {
+        const int t0 = c * B, b = std::min(B, n_pairs - t0), par = c & 1;
+        if (c + 1 < n_chunks) if (int rc = upload(c + 1)) return rc;
+        CU(cudaStreamWaitEvent(sc, ctx->ev_h2d[par], 0));
+        if (c == 0) expand_frames(ctx, L, pl.f0, n, (size_t)W, 0, 1);
+        expand_frames(ctx, L, pl.fstage[par], n, (size_t)W, t0 + 1, b);
+        CU(cudaEventRecord(ctx->ev_frame_free[par], sc));
+        if (c >= 2) CU(cudaStreamWaitEvent(sc, ctx->ev_out_free[par], 0));
+        solve_pairs(ctx, L, t0, b, pl.flow0[par], n);
+        if (bgr) picture(ctx, L, pl.flow0[par], n, n, pl.bgr[par], n * 3, b);
+        if (magsum) launch_sum_magnitude_batch(L, pl.flow0[par], n, n, ctx->sumacc, d_sums + t0, b);
+        CU(cudaEventRecord(ctx->ev_out_ready[par], sc));
+        CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
+        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[par], (size_t)b * n * 3, cudaMemcpyDeviceToHost, sd));
+        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[par], (size_t)b * n * 8, cudaMemcpyDeviceToHost, sd));
+        CU(cudaEventRecord(ctx->ev_out_free[par], sd));
     }
-    if (magsum) {
-        CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[(n_frames - 2) & 1], 0));
-        CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)(n_frames - 1), cudaMemcpyDeviceToHost, sd));
-    }
+    if (magsum) CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost, sd));
     CU(cudaEventRecord(ctx->ev_t1, sd));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(sd));
@@ -731,19 +871,38 @@ int ofb_stage_level_image(ofb_context* ctx, const void* frame, int dtype, int W,
     scale_geometry(W, H, pyr_scale, k, &Wk, &Hk, &ksize, &sigma, nullptr);
     int pitch = round_up(Wk, 32);
     size_t esz = dtype == OFB_U8 ? 1 : 4;
-    float *dfr, *dT, *dI, *dtaps;
+    float *dfr, *dT, *dI, *dtab;
     if (int rc = stage_buf(ctx, 0, (size_t)W * H * esz, &dfr)) return rc;
     if (int rc = stage_buf(ctx, 1, sizeof(float) * (size_t)H * pitch, &dT)) return rc;
     if (int rc = stage_buf(ctx, 2, sizeof(float) * (size_t)Hk * pitch, &dI)) return rc;
-    if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)ksize, &dtaps)) return rc;
     std::vector<float> taps;
     gaussian_taps(ksize, sigma, taps);
+    std::vector<int> ix, iy; std::vector<float> wx, wy;
+    linear_table(Wk, W, ix, wx);
+    linear_table(Hk, H, iy, wy);
+    // one staging block: taps | sx | ax | sy | ay
+    size_t o_taps = 0, o_sx = o_taps + taps.size(), o_ax = o_sx + ix.size(), o_sy = o_ax + wx.size(), o_ay = o_sy + iy.size();
+    if (int rc = stage_buf(ctx, 3, sizeof(float) * (o_ay + wy.size()), &dtab)) return rc;
     cudaStream_t s = ctx->s_compute;
-    CU(cudaMemcpyAsync(dtaps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dtab + o_taps, taps.data(), 4 * taps.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dtab + o_sx, ix.data(), 4 * ix.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dtab + o_ax, wx.data(), 4 * wx.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dtab + o_sy, iy.data(), 4 * iy.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dtab + o_ay, wy.data(), 4 * wy.size(), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(dfr, frame, (size_t)W * H * esz, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));      // host vectors go out of scope below
     Launch L{s, &ctx->prof};
-    launch_pyr_h(L, dfr, dtype, W, H, (size_t)W * esz, dtaps, ksize, dT, Wk, pitch);
-    launch_pyr_v(L, dT, H, pitch, dtaps, ksize, dI, Wk, Hk, pitch);
+    if (ctx->generic) {
+        launch_pyr_h(L, dfr, dtype, W, H, (size_t)W * esz, dtab + o_taps, ksize, dT, Wk, pitch);
+        launch_pyr_v(L, dT, H, pitch, dtab + o_taps, ksize, dI, Wk, Hk, pitch);
+    } else {
+        PyrArgs py{};
+        py.src = dfr; py.src_item = 0; py.src_pitch = (size_t)W * esz;
+        py.W = W; py.H = H; py.Wk = Wk; py.Hk = Hk; py.ksize = ksize; py.taps = dtab + o_taps;
+        py.sx = (const int*)(dtab + o_sx); py.ax = dtab + o_ax; py.sy = (const int*)(dtab + o_sy); py.ay = dtab + o_ay;
+        py.T = dT; py.t_item = 0; py.I = dI; py.i_item = 0; py.pitch = pitch;
+        launch_pyr2(L, dtype, py, 1);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpy2DAsync(out, sizeof(float) * Wk, dI, sizeof(float) * pitch, sizeof(float) * Wk, Hk, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -767,11 +926,20 @@ int ofb_stage_polyexp(ofb_context* ctx, const float* img, int W, int H, int poly
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(dtab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpy2DAsync(dI, sizeof(float) * pitch, img, sizeof(float) * W, sizeof(float) * W, H, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
     int len = 2 * poly_n + 1;
     PolyConst pc{dtab, dtab + len, dtab + 2 * len, poly_n, ig[0], ig[1], ig[2], ig[3]};
     Launch L{s, &ctx->prof};
     Planes5 Rp{dR, plane, pitch};
-    launch_polyexp(L, dI, W, H, pitch, pc, dtmp, Rp, ctx->generic);
+    if (!ctx->generic && polyexp2_supported(poly_n)) {
+        PolyArgs a;
+        fill_poly_args(a, poly_n, tab, ig);
+        a.src = dI; a.src_item = 0; a.src_pitch = sizeof(float) * (size_t)pitch; a.W = W; a.H = H;
+        a.R = SlotRing{dR, 5 * plane, plane, pitch, 1}; a.slot0 = 0;
+        launch_polyexp2(L, 0, a, 1);
+    } else {
+        launch_polyexp(L, dI, W, H, pitch, pc, dtmp, Rp, ctx->generic);
+    }
     launch_interleave5(L, Rp, W, H, dout);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(R, dout, sizeof(float) * 5 * (size_t)W * H, cudaMemcpyDeviceToHost, s));
@@ -785,21 +953,28 @@ int ofb_stage_update_matrices(ofb_context* ctx, const float* R0, const float* R1
     CU(cudaSetDevice(ctx->device));
     int pitch = round_up(W, 32);
     size_t plane = (size_t)H * pitch, n = (size_t)W * H;
-    float *din, *dR0, *dR1, *dM, *dfl;
+    float *din, *dR, *dM, *dfl;
     if (int rc = stage_buf(ctx, 0, sizeof(float) * 5 * n, &din)) return rc;
-    if (int rc = stage_buf(ctx, 1, sizeof(float) * 5 * plane, &dR0)) return rc;
-    if (int rc = stage_buf(ctx, 2, sizeof(float) * 5 * plane, &dR1)) return rc;
+    if (int rc = stage_buf(ctx, 1, sizeof(float) * 10 * plane, &dR)) return rc;     // two slots
     if (int rc = stage_buf(ctx, 3, sizeof(float) * 5 * plane, &dM)) return rc;
     if (int rc = stage_buf(ctx, 4, sizeof(float) * 2 * n, &dfl)) return rc;
     cudaStream_t s = ctx->s_compute;
     Launch L{s, &ctx->prof};
-    Planes5 p0{dR0, plane, pitch}, p1{dR1, plane, pitch}, pm{dM, plane, pitch};
+    Planes5 p0{dR, plane, pitch}, p1{dR + 5 * plane, plane, pitch}, pm{dM, plane, pitch};
     CU(cudaMemcpyAsync(din, R0, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
     launch_deinterleave5(L, din, W, H, p0);
     CU(cudaMemcpyAsync(din, R1, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
     launch_deinterleave5(L, din, W, H, p1);
     CU(cudaMemcpyAsync(dfl, flow, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
-    launch_update_matrices(L, p0, p1, (const float2*)dfl, W, H, pm);
+    if (ctx->generic) {
+        launch_update_matrices(L, p0, p1, (const float2*)dfl, W, H, pm);
+    } else {
+        Um0Args u{};
+        u.flow = (const float2*)dfl; u.flow_item = 0;
+        u.R = SlotRing{dR, 5 * plane, plane, pitch, 2}; u.slot0 = 0;
+        u.M = dM; u.m_item = 0; u.plane = plane; u.pitch = pitch; u.W = W; u.H = H;
+        launch_um0(L, 1, u, 1);
+    }
     launch_interleave5(L, pm, W, H, din);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(M, din, sizeof(float) * 5 * n, cudaMemcpyDeviceToHost, s));
@@ -826,9 +1001,19 @@ int ofb_stage_blur_solve(ofb_context* ctx, const float* M, int W, int H, int win
     Planes5 pm{dM, plane, pitch};
     CU(cudaMemcpyAsync(dk, gk.data(), sizeof(float) * gk.size(), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(din, M, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
     launch_deinterleave5(L, din, W, H, pm);
-    if (gaussian) launch_blur_solve_gauss(L, pm, W, H, winsize, dk, dtmp, (float2*)dfl, ctx->generic);
-    else launch_blur_solve_box(L, pm, W, H, winsize, (double*)dtmp, (float2*)dfl, ctx->generic);
+    if (gaussian) {
+        launch_blur_solve_gauss(L, pm, W, H, winsize, dk, dtmp, (float2*)dfl, true);
+    } else if (!ctx->generic && iter_supported(winsize)) {
+        IterArgs a{};
+        a.Min = dM; a.Mout = nullptr; a.m_item = 0; a.plane = plane; a.pitch = pitch;
+        a.flow = (float2*)dfl; a.flow_item = 0; a.W = W; a.H = H;
+        a.c = (float)(1e-3 * (double)winsize * winsize * winsize * winsize);
+        launch_iter(L, a, winsize, false, 1, ctx->sm_count);
+    } else {
+        launch_blur_solve_box(L, pm, W, H, winsize, (double*)dtmp, (float2*)dfl, true);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(flow, dfl, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -857,6 +1042,8 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
 {
     if (!ctx || !name) return OFB_ERR_BAD_ARG;
     if (!strcmp(name, "generic_kernels")) { ctx->generic = value != 0; return OFB_OK; }
+    if (!strcmp(name, "batch")) { ctx->batch = std::max(1, std::min(value, MAX_BATCH)); return OFB_OK; }
+    if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "profile")) {
         cudaSetDevice(ctx->device);
         cudaDeviceSynchronize();

@@ -1,0 +1,242 @@
+// iter.cu -- the per-scale iteration of cv2.calcOpticalFlowFarneback (call
+// sites /root/reference/optical_flow.py:51, visualize_optical_flow.py:38), batched over frame pairs.
+//
+//   k_um0<SRC>      first UpdateMatrices of a scale, fused with the inter-scale flow initialisation
+//                   (zeros | an existing flow | bilinear up-sample of the coarser flow * 1/pyr_scale).
+//   k_iter<M,FUSE>  FarnebackUpdateFlow_Blur for a box window of half-width M:
+//                     blur(M_in) -> 2x2 solve -> flow                       (FUSE = false, last iteration)
+//                     blur(M_in) -> 2x2 solve -> UpdateMatrices -> M_out    (FUSE = true; the flow of a middle
+//                                                                           iteration never leaves registers)
+//
+// k_iter: one CTA owns TW = 96-2M output columns and walks down a strip of rows in steps of R = 2M+1.
+//   V phase  thread = (channel, column).  The R rows entering the window are loaded once (coalesced) into
+//            registers; window sums for the R rows of the step come from suffix sums of the previous block
+//            and prefix sums of the new one (van Herk / Gil-Werman): 3 FADD per row, no re-read of M.
+//   H phase  thread = (channel, row, segment of R outputs): the same trick along x out of shared memory.
+//   S phase  thread = pixel: determinant and numerators by Kahan's FMA-compensated a*d-b*c in f32
+//            (error <= 1.5 ulp of the exact f32-input result), one IEEE division each, then (FUSE) the
+//            per-pixel UpdateMatrices with its bilinear gather of R1.
+// Precision: cv2 keeps f64 running sums and an f64 solve.  Here every window sum is a <= 2R-term f32 sum
+// (no running sum over the image, so no drift) and the solve is compensated; measured endpoint difference
+// vs cv2 stays at the 1e-6 px level (tests/test_gpu_parity.py), four orders inside the tolerance.
+// The f32->f64 conversions this avoids ran on the 16-lane XU pipe and were the bottleneck of the first
+// version (profiles/r1_ncu_first.md).
+// Roofline: HBM.  Algorithmic bytes per pixel: 28 (FUSE=false), 96 (FUSE=true), 68 (k_um0).
+#include "common.cuh"
+#include "launch.cuh"
+#include "um_device.cuh"
+#include <algorithm>
+
+namespace ofb {
+
+// ------------------------------------------------------------------------------------------------
+// k_um0
+// ------------------------------------------------------------------------------------------------
+template <int SRC>   // 0 zero flow, 1 read flow, 2 up-sample coarse flow
+__global__ void __launch_bounds__(256)
+k_um0(Um0Args a)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, z = blockIdx.z;
+    if (x >= a.W || y >= a.H) return;
+    float dx = 0.f, dy = 0.f;
+    if (SRC == 1) {
+        float2 d = a.flow[(size_t)z * a.flow_item + (size_t)y * a.W + x];
+        dx = d.x; dy = d.y;
+    } else if (SRC == 2) {
+        const float2* prev = a.flow + (size_t)z * a.flow_item;
+        float a1, b1;
+        int sx = linear_coord(x, a.sx_scale, a.Wp, &a1);
+        int sy = linear_coord(y, a.sy_scale, a.Hp, &b1);
+        float a0 = 1.f - a1, b0 = 1.f - b1;
+        int sx1 = min(sx + 1, a.Wp - 1), sy1 = min(sy + 1, a.Hp - 1);
+        float2 p00 = prev[(size_t)sy * a.Wp + sx], p01 = prev[(size_t)sy * a.Wp + sx1];
+        float2 p10 = prev[(size_t)sy1 * a.Wp + sx], p11 = prev[(size_t)sy1 * a.Wp + sx1];
+        float hx0 = p00.x * a0 + p01.x * a1, hx1 = p10.x * a0 + p11.x * a1;
+        float hy0 = p00.y * a0 + p01.y * a1, hy1 = p10.y * a0 + p11.y * a1;
+        dx = (hx0 * b0 + hx1 * b1) * a.mul;
+        dy = (hy0 * b0 + hy1 * b1) * a.mul;
+    }
+    const int s0 = (a.slot0 + z) % a.R.nslots, s1 = (s0 + 1) % a.R.nslots;
+    M5 m = um_pixel(x, y, dx, dy, a.R.slot(s0), a.R.slot(s1), a.W, a.H);
+    float* out = a.M + (size_t)z * a.m_item + (size_t)y * a.pitch + x;
+#pragma unroll
+    for (int c = 0; c < 5; c++) out[(size_t)c * a.plane] = m.v[c];
+}
+
+void launch_um0(Launch& L, int src, const Um0Args& a, int batch)
+{
+    dim3 block(32, 8), grid(divup(a.W, 32), divup(a.H, 8), batch);
+    const char* names[3] = {"um0_zero", "um0_flow", "um0_upsample"};
+    L.run(names[src], [&](cudaStream_t s) {
+        if (src == 0) k_um0<0><<<grid, block, 0, s>>>(a);
+        else if (src == 1) k_um0<1><<<grid, block, 0, s>>>(a);
+        else k_um0<2><<<grid, block, 0, s>>>(a);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_iter
+// ------------------------------------------------------------------------------------------------
+constexpr int IT_CW = 96;                 // columns loaded per CTA (3 warps per channel)
+constexpr int IT_THREADS = 5 * IT_CW;     // 480
+constexpr int IT_VP = IT_CW + 1;          // odd pitch of the V buffer
+
+__device__ __forceinline__ float kahan_det(float a, float d, float b, float c)   // a*d - b*c
+{
+    float w = __fmul_rn(b, c);
+    float e = __fmaf_rn(-b, c, w);
+    float f = __fmaf_rn(a, d, -w);
+    return __fadd_rn(f, e);
+}
+
+template <int M, bool FUSE>
+__global__ void __launch_bounds__(IT_THREADS, (M <= 8) ? 2 : 1)
+k_iter(IterArgs a)
+{
+    constexpr int R = 2 * M + 1;
+    constexpr int TW = IT_CW - 2 * M;
+    constexpr int HP = TW + 1;
+    constexpr int NSEG = (TW + R - 1) / R;
+    extern __shared__ float it_smem[];
+    float* sV = it_smem;                      // 5 * R * IT_VP
+    float* sH = it_smem + 5 * R * IT_VP;      // 5 * R * HP
+
+    const int tid = threadIdx.x, z = blockIdx.z;
+    const int W = a.W, H = a.H;
+    const int x0 = blockIdx.x * TW;
+    const int ybeg = blockIdx.y * a.strip_rows;
+    const int yend = min(ybeg + a.strip_rows, H);
+    if (ybeg >= H) return;
+
+    const int vc = tid / IT_CW, vcol = tid - vc * IT_CW;
+    const int gx = min(max(x0 - M + vcol, 0), W - 1);                 // replicate border in x
+    const float* __restrict__ src = a.Min + (size_t)z * a.m_item + (size_t)vc * a.plane + gx;
+    const int pitch = a.pitch;
+
+    float blkA[R];                                                     // rows ys-M .. ys+M of this column
+#pragma unroll
+    for (int i = 0; i < R; i++) blkA[i] = src[(size_t)min(max(ybeg - M + i, 0), H - 1) * pitch];
+
+    Planes5 R0{nullptr, 0, 0}, R1{nullptr, 0, 0};
+    float* mout = nullptr;
+    float2* fout = nullptr;
+    if (FUSE) {
+        const int s0 = (a.slot0 + z) % a.R.nslots, s1 = (s0 + 1) % a.R.nslots;
+        R0 = a.R.slot(s0); R1 = a.R.slot(s1);
+        mout = a.Mout + (size_t)z * a.m_item;
+    } else {
+        fout = a.flow + (size_t)z * a.flow_item;
+    }
+
+    for (int ys = ybeg; ys < yend; ys += R) {
+        // ---- V phase ----
+        float blkB[R];                                                 // rows ys+M+1 .. ys+3M+1
+#pragma unroll
+        for (int r = 0; r < R; r++) blkB[r] = src[(size_t)min(ys + M + 1 + r, H - 1) * pitch];
+#pragma unroll
+        for (int i = R - 2; i >= 0; i--) blkA[i] = __fadd_rn(blkA[i], blkA[i + 1]);      // suffix sums
+        {
+            float* v = sV + vc * R * IT_VP + vcol;
+            v[0] = blkA[0];
+            float p = blkB[0];
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                v[r * IT_VP] = __fadd_rn(blkA[r], p);
+                p = __fadd_rn(p, blkB[r]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; i++) blkA[i] = blkB[i];
+        __syncthreads();
+
+        // ---- H phase: item = (channel*R + row, segment) ----
+        if (tid < 5 * R * NSEG) {
+            const int seg = tid % NSEG, rc = tid / NSEG;
+            const int xa = seg * R;
+            const float* v = sV + rc * IT_VP + xa;
+            float* h = sH + rc * HP + xa;
+            float sa[R];
+#pragma unroll
+            for (int i = 0; i < R; i++) sa[i] = (xa + i < IT_CW) ? v[i] : 0.f;
+#pragma unroll
+            for (int i = R - 2; i >= 0; i--) sa[i] = __fadd_rn(sa[i], sa[i + 1]);
+            if (xa < TW) h[0] = sa[0];
+            float p = 0.f;
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                if (xa + r < TW) {
+                    float nb = v[R + r - 1];                           // column xa+r+2M <= CW-1
+                    p = (r == 1) ? nb : __fadd_rn(p, nb);
+                    h[r] = __fadd_rn(sa[r], p);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- S phase: item = pixel ----
+        for (int i = tid; i < R * TW; i += IT_THREADS) {
+            const int r = i / TW, lx = i - r * TW;
+            const int y = ys + r, x = x0 + lx;
+            if (y < yend && x < W) {
+                const float* h = sH + r * HP + lx;
+                const float g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
+                // flow = [g11*h2 - g12*h1, g22*h1 - g12*h2] * scale^2 / ((g11*g22 - g12^2) * scale^2 + 1e-3)
+                //      = [ ... ] / (g11*g22 - g12^2 + 1e-3 / scale^2)
+                const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
+                const float fx = __fdiv_rn(kahan_det(g11, h2, g12, h1), det);
+                const float fy = __fdiv_rn(kahan_det(g22, h1, g12, h2), det);
+                if (FUSE) {
+                    M5 m = um_pixel(x, y, fx, fy, R0, R1, W, H);
+                    float* o = mout + (size_t)y * pitch + x;
+#pragma unroll
+                    for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
+                } else {
+                    fout[(size_t)y * W + x] = make_float2(fx, fy);
+                }
+            }
+        }
+        // no barrier here: the next V phase writes only sV (last read before the barrier above); sH is
+        // next written after the barrier that follows that V phase.
+    }
+}
+
+template <int M, bool FUSE>
+static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
+{
+    constexpr int R = 2 * M + 1, TW = IT_CW - 2 * M, HP = TW + 1;
+    const size_t smem = sizeof(float) * (5 * R * IT_VP + 5 * R * HP);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_iter<M, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int xt = divup(a.W, TW);
+    // aim at >= 2 CTAs per SM for ONE pair; strips are whole steps of R rows.  The partition must not depend
+    // on the batch size: the van Herk blocks restart at strip boundaries, so it fixes the f32 rounding, and a
+    // pair must give bit-identical results whether it is processed alone or inside a batch.
+    int want = std::max(1, (2 * sm_count + xt - 1) / xt);
+    int strip = divup(divup(a.H, want), R) * R;
+    strip = std::max(strip, std::min(a.H, 2 * R));          // keep the block-A preload amortised
+    strip = divup(strip, R) * R;
+    a.strip_rows = strip;
+    dim3 grid(xt, divup(a.H, strip), batch);
+    L.run(FUSE ? "iter_fused" : "iter_last", [&](cudaStream_t s) {
+        k_iter<M, FUSE><<<grid, IT_THREADS, smem, s>>>(a);
+    });
+}
+
+bool iter_supported(int winsize) { int m = winsize / 2; return m >= 1 && m <= 16; }
+
+void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count)
+{
+    const int m = winsize / 2;
+    switch (m) {
+#define OFB_CASE(MM) case MM: if (fuse_um) run_iter<MM, true>(L, a, batch, sm_count); else run_iter<MM, false>(L, a, batch, sm_count); return;
+        OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
+        OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)
+#undef OFB_CASE
+        default: break;
+    }
+}
+
+}  // namespace ofb

@@ -159,4 +159,211 @@ void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const Po
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_polyexp2<N, SRC>: unrolled (compile-time poly_n), batched over frames (blockIdx.z), optional fused
+// scale-0 pre-blur.
+//
+//   SRC 0  input is a level image I (f32).
+//   SRC 1  input is the u8 frame itself and the level is scale 0: the [1/4 1/2 1/4] x [1/4 1/2 1/4]
+//          pre-blur of A.3 (reflect-101) is applied while the patch is staged, in the order of the
+//          stand-alone pyramid kernels (row pass, then column pass), so I_0 never goes to HBM.
+//   SRC 2  the same for an f32 frame.
+//
+// Vertical pass in f32 exactly as cv2; its three results are widened to f64 ONCE per element when they
+// are stored to shared memory (3 conversions per element instead of ~28 per output pixel -- f32<->f64
+// conversions run on the 16-lane XU pipe and bounded the first version).  The horizontal pass then runs
+// entirely in f64 with DFMA.  cv2 forms (a+b), (a-b) and four of the six products in f32 before
+// widening; doing them in f64 differs from cv2 by that f32 rounding (<= 2^-24 relative per term).
+// Horizontal pass: lane -> (row = lane % 16, block of 4 consecutive outputs); the odd f64 row pitch
+// keeps the 16 rows of a half-warp on distinct bank pairs, and each thread re-uses its 4+2N-wide
+// register window for 4 outputs.
+// ------------------------------------------------------------------------------------------------
+template <int N, int SRC>
+__global__ void __launch_bounds__(256, 2)
+k_polyexp2(PolyArgs a)
+{
+    constexpr int TW = 64, TH = 16;
+    constexpr int PW = TW + 2 * N, PH = TH + 2 * N;
+    constexpr int RP = (PW | 1);                       // odd pitch (in doubles) of the vertical-pass results
+    constexpr int RAWW = PW + 2, RAWH = PH + 2;
+    extern __shared__ __align__(16) unsigned char pe_smem[];
+    double* sR0 = reinterpret_cast<double*>(pe_smem);  // TH x RP each
+    double* sR1 = sR0 + TH * RP;
+    double* sR2 = sR1 + TH * RP;
+    float* sI = reinterpret_cast<float*>(sR2 + TH * RP);        // PH x PW   (SRC != 0: aliases the raw patch)
+    float* sHB = sI + RAWH * RAWW;                                // RAWH x PW (SRC != 0 only)
+
+    const int tid = threadIdx.x, z = blockIdx.z;
+    const int W = a.W, H = a.H;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const unsigned char* srcb = (const unsigned char*)a.src + (size_t)z * a.src_item;
+
+    if (SRC == 0) {
+        for (int i = tid; i < PH * PW; i += 256) {
+            int py = i / PW, px = i - py * PW;
+            int gy = min(max(y0 + py - N, 0), H - 1), gx = min(max(x0 + px - N, 0), W - 1);
+            sI[i] = ((const float*)(srcb + (size_t)gy * a.src_pitch))[gx];
+        }
+        __syncthreads();
+    } else {
+        // raw patch: raw[j][i] = frame(reflect101(y0-N-1+j), reflect101(x0-N-1+i))
+        float* raw = sI;
+        const int ubx = x0 - N - 1, uby = y0 - N - 1;
+        for (int i = tid; i < RAWH * RAWW; i += 256) {
+            int j = i / RAWW, ii = i - j * RAWW;
+            int fy = reflect101(uby + j, H), fx = reflect101(ubx + ii, W);
+            const unsigned char* row = srcb + (size_t)fy * a.src_pitch;
+            raw[i] = (SRC == 1) ? (float)row[fx] : ((const float*)row)[fx];
+        }
+        __syncthreads();
+        // row pass at the (replicate-clamped) patch columns
+        for (int i = tid; i < RAWH * PW; i += 256) {
+            int j = i / PW, px = i - j * PW;
+            int cx = min(max(x0 - N + px, 0), W - 1) - ubx;            // raw column of the centre tap
+            const float* r = raw + j * RAWW + cx;
+            float acc = 0.25f * r[-1];
+            acc = acc + 0.5f * r[0];
+            acc = acc + 0.25f * r[1];
+            sHB[i] = acc;
+        }
+        __syncthreads();
+        // column pass at the (replicate-clamped) patch rows; overwrites the raw patch
+        for (int i = tid; i < PH * PW; i += 256) {
+            int py = i / PW, px = i - py * PW;
+            int cy = min(max(y0 - N + py, 0), H - 1) - uby;
+            const float* c = sHB + cy * PW + px;
+            float acc = 0.25f * c[-PW];
+            acc = acc + 0.5f * c[0];
+            acc = acc + 0.25f * c[PW];
+            sI[i] = acc;
+        }
+        __syncthreads();
+    }
+
+    // ---- vertical pass (f32, cv2's order), results widened once ----
+    for (int i = tid; i < TH * PW; i += 256) {
+        int ty = i / PW, px = i - ty * PW;
+        const float* col = sI + (ty + N) * PW + px;
+        float r0 = col[0] * a.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= N; k++) {
+            float lo = col[-k * PW], hi = col[k * PW];
+            float p = lo + hi;
+            r0 = r0 + a.g[k] * p;
+            r1 = r1 + a.xg[k] * (hi - lo);
+            r2 = r2 + a.xxg[k] * p;
+        }
+        sR0[ty * RP + px] = (double)r0;
+        sR1[ty * RP + px] = (double)r1;
+        sR2[ty * RP + px] = (double)r2;
+    }
+    __syncthreads();
+
+    // ---- horizontal pass (f64) ----
+    const int lane = tid & 31, warp = tid >> 5;
+    const int ly = lane & 15;
+    const int xb = warp * 2 + (lane >> 4);              // 0..15
+    const int lx0 = xb * 4;
+    const int gy = y0 + ly, gx0 = x0 + lx0;
+    if (gy >= H || gx0 >= W) return;
+    double b1[4], b2[4], b3[4], b4[4], b5[4], b6[4];
+    {
+        double w[4 + 2 * N];
+        const double* q = sR0 + ly * RP + lx0;          // element j of the window = patch column lx0 + j
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double s1 = w[o + N] * a.gd[0], s2 = 0, s4 = 0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                double tg = w[o + N + k] + w[o + N - k];
+                s1 = fma(tg, a.gd[k], s1);
+                s4 = fma(tg, a.xxgd[k], s4);
+                s2 = fma(w[o + N + k] - w[o + N - k], a.xgd[k], s2);
+            }
+            b1[o] = s1; b2[o] = s2; b4[o] = s4;
+        }
+        q = sR1 + ly * RP + lx0;
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double s3 = w[o + N] * a.gd[0], s6 = 0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                s3 = fma(w[o + N + k] + w[o + N - k], a.gd[k], s3);
+                s6 = fma(w[o + N + k] - w[o + N - k], a.xgd[k], s6);
+            }
+            b3[o] = s3; b6[o] = s6;
+        }
+        q = sR2 + ly * RP + lx0;
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double s5 = w[o + N] * a.gd[0];
+#pragma unroll
+            for (int k = 1; k <= N; k++) s5 = fma(w[o + N + k] + w[o + N - k], a.gd[k], s5);
+            b5[o] = s5;
+        }
+    }
+    float o0[4], o1[4], o2[4], o3[4], o4[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        o0[o] = (float)(b3[o] * a.ig11);
+        o1[o] = (float)(b2[o] * a.ig11);
+        o2[o] = (float)fma(b5[o], a.ig33, b1[o] * a.ig03);
+        o3[o] = (float)fma(b4[o], a.ig33, b1[o] * a.ig03);
+        o4[o] = (float)(b6[o] * a.ig55);
+    }
+    const int slot = (a.slot0 + z) % a.R.nslots;
+    float* out = a.R.base + (size_t)slot * a.R.slot_stride + (size_t)gy * a.R.pitch + gx0;
+    const size_t pl = a.R.plane;
+    if (gx0 + 3 < W) {
+        *reinterpret_cast<float4*>(out) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<float4*>(out + pl) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+        *reinterpret_cast<float4*>(out + 2 * pl) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        *reinterpret_cast<float4*>(out + 3 * pl) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+        *reinterpret_cast<float4*>(out + 4 * pl) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+            if (gx0 + o < W) {
+                out[o] = o0[o]; out[pl + o] = o1[o]; out[2 * pl + o] = o2[o]; out[3 * pl + o] = o3[o]; out[4 * pl + o] = o4[o];
+            }
+    }
+}
+
+template <int N, int SRC>
+static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
+{
+    constexpr int TW = 64, TH = 16, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1);
+    size_t smem = sizeof(double) * 3 * TH * RP +
+                  sizeof(float) * (SRC == 0 ? (size_t)PH * PW : (size_t)(PH + 2) * (PW + 2) + (size_t)(PH + 2) * PW);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_polyexp2<N, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    dim3 grid(divup(a.W, TW), divup(a.H, TH), batch);
+    const char* nm = SRC == 0 ? "polyexp_level" : "polyexp_scale0";
+    L.run(nm, [&](cudaStream_t s) { k_polyexp2<N, SRC><<<grid, 256, smem, s>>>(a); });
+}
+
+bool polyexp2_supported(int n) { return n == 3 || n == 5 || n == 7; }
+
+void launch_polyexp2(Launch& L, int src_kind, const PolyArgs& a, int batch)
+{
+#define OFB_PE(NN)                                                       \
+    case NN:                                                             \
+        if (src_kind == 0) run_polyexp2<NN, 0>(L, a, batch);             \
+        else if (src_kind == 1) run_polyexp2<NN, 1>(L, a, batch);        \
+        else run_polyexp2<NN, 2>(L, a, batch);                           \
+        return;
+    switch (a.n) { OFB_PE(3) OFB_PE(5) OFB_PE(7) default: break; }
+#undef OFB_PE
+}
+
 }  // namespace ofb

@@ -100,4 +100,94 @@ void launch_pyr_v(Launch& L, const float* T, int H, int t_pitch, const float* ta
     });
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Batched variants (blockIdx.z = frame of the batch).  The bilinear source index / weight of every
+// destination column and row is a property of the level, so the engine builds it once per plan on
+// the host (same double-precision rule as linear_coord) instead of per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pyr_h2(PyrArgs a)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, r = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (x >= a.Wk || r >= a.H) return;
+    const int W = a.W, ksize = a.ksize, c = ksize / 2;
+    const int sx = a.sx[x];
+    const float a1 = a.ax[x], a0 = 1.f - a1;
+    const T* row = (const T*)((const char*)a.src + (size_t)z * a.src_item + (size_t)r * a.src_pitch);
+    const float* __restrict__ taps = a.taps;
+    float b0 = 0.f, b1 = 0.f;
+    if (sx - c >= 0 && sx + 1 + c < W) {
+        const T* p = row + sx - c;
+        if (a1 != 0.f) {
+            float prev = (float)p[0];
+            for (int j = 0; j < ksize; j++) {
+                float cur = (float)p[j + 1];
+                float t = __ldg(taps + j);
+                b0 += t * prev;
+                b1 += t * cur;
+                prev = cur;
+            }
+        } else {
+            for (int j = 0; j < ksize; j++) b0 += __ldg(taps + j) * (float)p[j];
+        }
+    } else {
+        int sx1 = min(sx + 1, W - 1);
+        for (int j = 0; j < ksize; j++) {
+            float t = __ldg(taps + j);
+            b0 += t * (float)row[reflect101(sx + j - c, W)];
+            if (a1 != 0.f) b1 += t * (float)row[reflect101(sx1 + j - c, W)];
+        }
+    }
+    a.T[(size_t)z * a.t_item + (size_t)r * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
+}
+
+__global__ void __launch_bounds__(256)
+k_pyr_v2(PyrArgs a)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (x >= a.Wk || y >= a.Hk) return;
+    const int H = a.H, ksize = a.ksize, c = ksize / 2;
+    const int sy = a.sy[y];
+    const float a1 = a.ay[y], a0 = 1.f - a1;
+    const int sy1 = min(sy + 1, H - 1);
+    const float* T = a.T + (size_t)z * a.t_item + x;
+    const float* __restrict__ taps = a.taps;
+    float b0 = 0.f, b1 = 0.f;
+    if (sy - c >= 0 && sy + 1 + c < H) {
+        const float* p = T + (size_t)(sy - c) * a.pitch;
+        if (a1 != 0.f) {
+            float prev = p[0];
+            for (int j = 0; j < ksize; j++) {
+                float cur = p[(size_t)(j + 1) * a.pitch];
+                float t = __ldg(taps + j);
+                b0 += t * prev;
+                b1 += t * cur;
+                prev = cur;
+            }
+        } else {
+            for (int j = 0; j < ksize; j++) b0 += __ldg(taps + j) * p[(size_t)j * a.pitch];
+        }
+    } else {
+        for (int j = 0; j < ksize; j++) {
+            float t = __ldg(taps + j);
+            b0 += t * T[(size_t)reflect101(sy + j - c, H) * a.pitch];
+            if (a1 != 0.f) b1 += t * T[(size_t)reflect101(sy1 + j - c, H) * a.pitch];
+        }
+    }
+    a.I[(size_t)z * a.i_item + (size_t)y * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
+}
+
+void launch_pyr2(Launch& L, int dtype, const PyrArgs& a, int batch)
+{
+    dim3 block(64, 4);
+    dim3 gh(divup(a.Wk, 64), divup(a.H, 4), batch), gv(divup(a.Wk, 64), divup(a.Hk, 4), batch);
+    L.run(dtype == 0 ? "pyr_h_u8" : "pyr_h_f32", [&](cudaStream_t s) {
+        if (dtype == 0) k_pyr_h2<uint8_t><<<gh, block, 0, s>>>(a);
+        else k_pyr_h2<float><<<gh, block, 0, s>>>(a);
+    });
+    L.run("pyr_v", [&](cudaStream_t s) { k_pyr_v2<<<gv, block, 0, s>>>(a); });
+}
+
 }  // namespace ofb

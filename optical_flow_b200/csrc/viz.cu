@@ -44,10 +44,16 @@ __device__ __forceinline__ float deg_to_rad_cv(float a) { return a * (float)(3.1
 // ---- per-frame min / max of the magnitude ------------------------------------------------------
 // Magnitudes are >= 0, so their IEEE bit patterns order like unsigned integers.
 __global__ void k_minmax_reset(unsigned* mm) { mm[0] = 0x7f800000u; mm[1] = 0u; }
+__global__ void k_minmax_reset_batch(unsigned* mm, int batch)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) { mm[2 * i] = 0x7f800000u; mm[2 * i + 1] = 0u; }
+}
 
 __global__ void __launch_bounds__(256)
-k_minmax_mag(const float2* __restrict__ flow, size_t n, unsigned* __restrict__ mm)
+k_minmax_mag(const float2* __restrict__ flow, size_t n, unsigned* __restrict__ mm, size_t flow_item = 0)
 {
+    flow += (size_t)blockIdx.y * flow_item; mm += 2 * blockIdx.y;
     float lo = __int_as_float(0x7f800000), hi = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float2 f = flow[i];
@@ -124,8 +130,10 @@ __device__ __forceinline__ uchar3 pixel_bgr(float2 f, NormCoef nc)
 
 // 4 pixels per thread: two 16-byte flow loads, three 4-byte picture stores.
 __global__ void __launch_bounds__(256)
-k_flow_to_bgr_v4(const float4* __restrict__ flow4, size_t n4, const unsigned* __restrict__ mm, uint32_t* __restrict__ bgr)
+k_flow_to_bgr_v4(const float4* __restrict__ flow4, size_t n4, const unsigned* __restrict__ mm, uint32_t* __restrict__ bgr,
+                 size_t flow_item4 = 0, size_t bgr_item4 = 0)
 {
+    flow4 += (size_t)blockIdx.y * flow_item4; bgr += (size_t)blockIdx.y * bgr_item4; mm += 2 * blockIdx.y;
     NormCoef nc = norm_coef(mm);
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
         float4 a = flow4[2 * g], b = flow4[2 * g + 1];
@@ -139,8 +147,10 @@ k_flow_to_bgr_v4(const float4* __restrict__ flow4, size_t n4, const unsigned* __
 }
 
 __global__ void __launch_bounds__(256)
-k_flow_to_bgr_scalar(const float2* __restrict__ flow, size_t n, const unsigned* __restrict__ mm, uint8_t* __restrict__ bgr)
+k_flow_to_bgr_scalar(const float2* __restrict__ flow, size_t n, const unsigned* __restrict__ mm, uint8_t* __restrict__ bgr,
+                     size_t flow_item = 0, size_t bgr_item = 0)
 {
+    flow += (size_t)blockIdx.y * flow_item; bgr += (size_t)blockIdx.y * bgr_item; mm += 2 * blockIdx.y;
     NormCoef nc = norm_coef(mm);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uchar3 p = pixel_bgr(flow[i], nc);
@@ -161,8 +171,9 @@ k_cart_to_polar(const float2* __restrict__ flow, size_t n, float* __restrict__ m
 
 // ---- np.sum(mag): f64 accumulation (NumPy's pairwise f32 sum agrees to ~1e-7 relative) ----------
 __global__ void __launch_bounds__(256)
-k_sum_magnitude(const float2* __restrict__ flow, size_t n, double* __restrict__ acc)
+k_sum_magnitude(const float2* __restrict__ flow, size_t n, double* __restrict__ acc, size_t flow_item = 0)
 {
+    flow += (size_t)blockIdx.y * flow_item; acc += blockIdx.y;
     double s = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float2 f = flow[i];
@@ -183,6 +194,16 @@ k_sum_magnitude(const float2* __restrict__ flow, size_t n, double* __restrict__ 
 }
 __global__ void k_sum_finish(const double* acc, float* out) { *out = (float)*acc; }
 __global__ void k_zero_double(double* p) { *p = 0.0; }
+__global__ void k_sum_finish_batch(const double* acc, float* out, int batch)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) out[i] = (float)acc[i];
+}
+__global__ void k_zero_double_batch(double* p, int batch)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) p[i] = 0.0;
+}
 
 static inline unsigned reduce_grid(size_t n, int per_thread)
 {
@@ -215,6 +236,35 @@ void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned*
             k_flow_to_bgr_scalar<<<reduce_grid(n, 4), 256, 0, s>>>(flow, n, minmax, bgr);
         });
     }
+}
+
+void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax,
+                          uint8_t* bgr, size_t bgr_item, int batch)
+{
+    L.run("minmax_reset", [&](cudaStream_t s) { k_minmax_reset_batch<<<divup(batch, 64), 64, 0, s>>>(minmax, batch); });
+    dim3 g1(reduce_grid(n, 8), batch);
+    L.run("minmax_mag", [&](cudaStream_t s) { k_minmax_mag<<<g1, 256, 0, s>>>(flow, n, minmax, flow_item); });
+    bool vec = (n % 4 == 0) && ((uintptr_t)flow % 16 == 0) && ((uintptr_t)bgr % 4 == 0) && (flow_item % 2 == 0) && (bgr_item % 4 == 0);
+    if (vec) {
+        size_t n4 = n / 4;
+        dim3 g2(reduce_grid(n4, 2), batch);
+        L.run("flow_to_bgr_v4", [&](cudaStream_t s) {
+            k_flow_to_bgr_v4<<<g2, 256, 0, s>>>((const float4*)flow, n4, minmax, (uint32_t*)bgr, flow_item / 2, bgr_item / 4);
+        });
+    } else {
+        dim3 g2(reduce_grid(n, 4), batch);
+        L.run("flow_to_bgr_scalar", [&](cudaStream_t s) {
+            k_flow_to_bgr_scalar<<<g2, 256, 0, s>>>(flow, n, minmax, bgr, flow_item, bgr_item);
+        });
+    }
+}
+
+void launch_sum_magnitude_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, double* acc, float* out, int batch)
+{
+    L.run("sum_zero", [&](cudaStream_t s) { k_zero_double_batch<<<divup(batch, 64), 64, 0, s>>>(acc, batch); });
+    dim3 g(reduce_grid(n, 8), batch);
+    L.run("sum_magnitude", [&](cudaStream_t s) { k_sum_magnitude<<<g, 256, 0, s>>>(flow, n, acc, flow_item); });
+    L.run("sum_finish", [&](cudaStream_t s) { k_sum_finish_batch<<<divup(batch, 64), 64, 0, s>>>(acc, out, batch); });
 }
 
 void launch_cart_to_polar(Launch& L, const float2* flow, size_t n, float* mag, float* ang)
