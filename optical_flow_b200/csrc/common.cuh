@@ -23,21 +23,37 @@ struct Planes5 {          // five planar f32 images
     __host__ __device__ float* ch(int c) const { return base + (size_t)c * plane; }
 };
 
-// Batched views: R planes of one pyramid level for a ring of frame slots; pair z of a batch reads the
-// slots (slot0+z) % nslots and (slot0+z+1) % nslots.
+// Polynomial-expansion coefficients R of one image: channels 0..3 (d/dy, d/dx, yy, xx) interleaved as one
+// float4 per pixel, channel 4 (xy) as a separate plane.  UpdateMatrices gathers R1 at 4 neighbours: with this
+// layout that is 4 x (LDG.128 + LDG.32) instead of 20 scalar loads, and a warp still reads whole 128-byte lines.
+struct RView {
+    float4* a;                  // H x pitch float4
+    float* b;                   // H x pitch float
+    int pitch;                  // pixels between rows (multiple of 32)
+};
+
+// Batched views: R of one pyramid level for a ring of frame slots; pair z of a batch reads the slots
+// (slot0+z) % nslots and (slot0+z+1) % nslots.  A slot is 5*plane floats: 4*plane of float4 data, then plane of ch 4.
 struct SlotRing {
     float* base;                // slot s at base + s * slot_stride
-    size_t slot_stride;         // floats
-    size_t plane;               // floats between the 5 planes of a slot
+    size_t slot_stride;         // floats (= 5 * plane)
+    size_t plane;               // pixels per plane (H * pitch)
     int pitch;
     int nslots;
-    __host__ __device__ Planes5 slot(int s) const { return Planes5{base + (size_t)s * slot_stride, plane, pitch}; }
+    __host__ __device__ RView slot(int s) const
+    {
+        float* p = base + (size_t)s * slot_stride;
+        return RView{reinterpret_cast<float4*>(p), p + 4 * plane, pitch};
+    }
+    __host__ __device__ int wrap(int s) const { return s >= nslots ? s - nslots : s; }   // s < 2 * nslots
 };
 
 // first UpdateMatrices of a scale (iter.cu k_um0); batch item z
 struct Um0Args {
     const float2* flow; size_t flow_item;   // SRC 1: flow of this scale; SRC 2: coarser flow (Wp x Hp); per-item stride in float2
-    int Wp, Hp; double sx_scale, sy_scale; float mul;
+    int Wp, Hp; float mul;
+    const int* ux; const float* uax;        // SRC 2: bilinear tables coarser -> this scale (per column / per row)
+    const int* uy; const float* uay;
     SlotRing R; int slot0;
     float* M; size_t m_item, plane; int pitch;
     int W, H;
@@ -117,7 +133,7 @@ void launch_pyr2(Launch& L, int dtype, const PyrArgs& a, int batch);
 // polyexp.cu -- A.5/A.6
 struct PolyConst { const float* g; const float* xg; const float* xxg; int n; double ig11, ig03, ig33, ig55; };
 void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const PolyConst& pc,
-                    float* tmp3 /* 3 planes */, Planes5 R, bool generic);
+                    float* tmp3 /* 3 planes */, RView R, bool generic);
 // batched, unrolled variant: src_kind 0 = level image (f32), 1 = u8 frame + fused [1/4 1/2 1/4]^2 pre-blur
 // (scale 0), 2 = f32 frame + the same pre-blur.  Returns false when poly_n has no unrolled instance.
 bool polyexp2_supported(int n);
@@ -127,7 +143,9 @@ void launch_polyexp2(Launch& L, int src_kind, const PolyArgs& a, int batch);
 void launch_upsample_flow(Launch& L, const float2* prev, int Wp, int Hp, float2* flow, int W, int H, float mul);
 void launch_area_flow(Launch& L, const float2* src, int Ws, int Hs, float2* dst, int Wd, int Hd, float mul);
 void launch_scale_flow(Launch& L, float2* flow, size_t n, float mul);
-void launch_update_matrices(Launch& L, Planes5 R0, Planes5 R1, const float2* flow, int W, int H, Planes5 M);
+void launch_update_matrices(Launch& L, RView R0, RView R1, const float2* flow, int W, int H, Planes5 M);
+void launch_r_interleave(Launch& L, RView src, int W, int H, float* dst /* (H,W,5) */);
+void launch_r_deinterleave(Launch& L, const float* src /* (H,W,5) */, int W, int H, RView dst);
 void launch_interleave5(Launch& L, Planes5 src, int W, int H, float* dst /* (H,W,5) */);
 void launch_deinterleave5(Launch& L, const float* src /* (H,W,5) */, int W, int H, Planes5 dst);
 

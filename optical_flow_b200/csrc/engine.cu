@@ -43,6 +43,8 @@ struct Level {
     float* taps = nullptr;              // device, ksize floats
     int* sx = nullptr; float* ax = nullptr;     // bilinear tables (k >= 1)
     int* sy = nullptr; float* ay = nullptr;
+    int* ux = nullptr; float* uax = nullptr;    // bilinear tables from scale k+1 to this scale (flow up-sample)
+    int* uy = nullptr; float* uay = nullptr;
     float* R = nullptr;                 // ring of nslots x 5 planes
     float2* flow = nullptr;             // batch x (H, W) float2 (k >= 1)
     size_t plane() const { return (size_t)H * pitch; }
@@ -294,6 +296,16 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
         if (int rc = dupload(ctx, pl, &l.sy, iy)) return rc;
         if (int rc = dupload(ctx, pl, &l.ay, wy)) return rc;
         if (int rc = dalloc(ctx, pl, &l.R, (size_t)pl.nslots * l.slot_stride())) return rc;
+        if (k < pl.K) {
+            int Wc, Hc, ksc; double sgc;
+            scale_geometry(W, H, p->pyr_scale, k + 1, &Wc, &Hc, &ksc, &sgc, nullptr);
+            linear_table(l.W, Wc, ix, wx);
+            linear_table(l.H, Hc, iy, wy);
+            if (int rc = dupload(ctx, pl, &l.ux, ix)) return rc;
+            if (int rc = dupload(ctx, pl, &l.uax, wx)) return rc;
+            if (int rc = dupload(ctx, pl, &l.uy, iy)) return rc;
+            if (int rc = dupload(ctx, pl, &l.uay, wy)) return rc;
+        }
         if (k > 0)
             if (int rc = dalloc(ctx, pl, &l.flow, B * l.flow_item())) return rc;
     }
@@ -330,7 +342,11 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
     return 0;
 }
 
-Planes5 slot_planes(const Level& l, int slot) { return Planes5{l.R + (size_t)slot * l.slot_stride(), l.plane(), l.pitch}; }
+RView slot_planes(const Level& l, int slot)
+{
+    float* p = l.R + (size_t)slot * l.slot_stride();
+    return RView{reinterpret_cast<float4*>(p), p + 4 * l.plane(), l.pitch};
+}
 SlotRing ring(const Plan& pl, const Level& l) { return SlotRing{l.R, l.slot_stride(), l.plane(), l.pitch, pl.nslots}; }
 Planes5 m_planes(const Plan& pl, const Level& l, int which, int item)
 {
@@ -409,7 +425,7 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                     src = 2;
                     u.flow = cl.flow + (size_t)z0 * cl.flow_item(); u.flow_item = cl.flow_item();
                     u.Wp = cl.W; u.Hp = cl.H;
-                    u.sx_scale = 1.0 / ((double)l.W / cl.W); u.sy_scale = 1.0 / ((double)l.H / cl.H);
+                    u.ux = l.ux; u.uax = l.uax; u.uy = l.uy; u.uay = l.uay;
                     u.mul = up_mul;
                 }
                 launch_um0(L, src, u, nb);
@@ -437,7 +453,7 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                 const Level& cl = pl.lv[k + 1];
                 launch_upsample_flow(L, cl.flow + (size_t)z * cl.flow_item(), cl.W, cl.H, fl, l.W, l.H, up_mul);
             }
-            Planes5 R0 = slot_planes(l, (slot0 + z) % pl.nslots), R1 = slot_planes(l, (slot0 + z + 1) % pl.nslots);
+            RView R0 = slot_planes(l, (slot0 + z) % pl.nslots), R1 = slot_planes(l, (slot0 + z + 1) % pl.nslots);
             Planes5 M = m_planes(pl, l, 0, 0);
             launch_update_matrices(L, R0, R1, fl, l.W, l.H, M);
             for (int i = 0; i < p.iterations; i++) {
@@ -930,7 +946,7 @@ int ofb_stage_polyexp(ofb_context* ctx, const float* img, int W, int H, int poly
     int len = 2 * poly_n + 1;
     PolyConst pc{dtab, dtab + len, dtab + 2 * len, poly_n, ig[0], ig[1], ig[2], ig[3]};
     Launch L{s, &ctx->prof};
-    Planes5 Rp{dR, plane, pitch};
+    RView Rp{reinterpret_cast<float4*>(dR), dR + 4 * plane, pitch};
     if (!ctx->generic && polyexp2_supported(poly_n)) {
         PolyArgs a;
         fill_poly_args(a, poly_n, tab, ig);
@@ -940,7 +956,7 @@ int ofb_stage_polyexp(ofb_context* ctx, const float* img, int W, int H, int poly
     } else {
         launch_polyexp(L, dI, W, H, pitch, pc, dtmp, Rp, ctx->generic);
     }
-    launch_interleave5(L, Rp, W, H, dout);
+    launch_r_interleave(L, Rp, W, H, dout);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(R, dout, sizeof(float) * 5 * (size_t)W * H, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -960,11 +976,13 @@ int ofb_stage_update_matrices(ofb_context* ctx, const float* R0, const float* R1
     if (int rc = stage_buf(ctx, 4, sizeof(float) * 2 * n, &dfl)) return rc;
     cudaStream_t s = ctx->s_compute;
     Launch L{s, &ctx->prof};
-    Planes5 p0{dR, plane, pitch}, p1{dR + 5 * plane, plane, pitch}, pm{dM, plane, pitch};
+    RView p0{reinterpret_cast<float4*>(dR), dR + 4 * plane, pitch};
+    RView p1{reinterpret_cast<float4*>(dR + 5 * plane), dR + 9 * plane, pitch};
+    Planes5 pm{dM, plane, pitch};
     CU(cudaMemcpyAsync(din, R0, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
-    launch_deinterleave5(L, din, W, H, p0);
+    launch_r_deinterleave(L, din, W, H, p0);
     CU(cudaMemcpyAsync(din, R1, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
-    launch_deinterleave5(L, din, W, H, p1);
+    launch_r_deinterleave(L, din, W, H, p1);
     CU(cudaMemcpyAsync(dfl, flow, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, s));
     if (ctx->generic) {
         launch_update_matrices(L, p0, p1, (const float2*)dfl, W, H, pm);

@@ -44,9 +44,8 @@ k_um0(Um0Args a)
         dx = d.x; dy = d.y;
     } else if (SRC == 2) {
         const float2* prev = a.flow + (size_t)z * a.flow_item;
-        float a1, b1;
-        int sx = linear_coord(x, a.sx_scale, a.Wp, &a1);
-        int sy = linear_coord(y, a.sy_scale, a.Hp, &b1);
+        const int sx = a.ux[x], sy = a.uy[y];
+        const float a1 = a.uax[x], b1 = a.uay[y];
         float a0 = 1.f - a1, b0 = 1.f - b1;
         int sx1 = min(sx + 1, a.Wp - 1), sy1 = min(sy + 1, a.Hp - 1);
         float2 p00 = prev[(size_t)sy * a.Wp + sx], p01 = prev[(size_t)sy * a.Wp + sx1];
@@ -56,7 +55,7 @@ k_um0(Um0Args a)
         dx = (hx0 * b0 + hx1 * b1) * a.mul;
         dy = (hy0 * b0 + hy1 * b1) * a.mul;
     }
-    const int s0 = (a.slot0 + z) % a.R.nslots, s1 = (s0 + 1) % a.R.nslots;
+    const int s0 = a.R.wrap(a.slot0 + z), s1 = a.R.wrap(s0 + 1);
     M5 m = um_pixel(x, y, dx, dy, a.R.slot(s0), a.R.slot(s1), a.W, a.H);
     float* out = a.M + (size_t)z * a.m_item + (size_t)y * a.pitch + x;
 #pragma unroll
@@ -117,11 +116,11 @@ k_iter(IterArgs a)
 #pragma unroll
     for (int i = 0; i < R; i++) blkA[i] = src[(size_t)min(max(ybeg - M + i, 0), H - 1) * pitch];
 
-    Planes5 R0{nullptr, 0, 0}, R1{nullptr, 0, 0};
+    RView R0{nullptr, nullptr, 0}, R1{nullptr, nullptr, 0};
     float* mout = nullptr;
     float2* fout = nullptr;
     if (FUSE) {
-        const int s0 = (a.slot0 + z) % a.R.nslots, s1 = (s0 + 1) % a.R.nslots;
+        const int s0 = a.R.wrap(a.slot0 + z), s1 = a.R.wrap(s0 + 1);
         R0 = a.R.slot(s0); R1 = a.R.slot(s1);
         mout = a.Mout + (size_t)z * a.m_item;
     } else {

@@ -8,6 +8,7 @@
 // upstream order of operations.  Roofline: HBM; algorithmic bytes 68 B/px (20+20+8 read, 20 written).
 #include "common.cuh"
 #include "launch.cuh"
+#include "um_device.cuh"
 
 namespace ofb {
 
@@ -99,52 +100,36 @@ __global__ void k_scale_flow(float2* flow, size_t n, float mul)
     if (i < n) { float2 v = flow[i]; v.x *= mul; v.y *= mul; flow[i] = v; }
 }
 
-// A.8
+// A.8 (per-pixel body in um_device.cuh)
 __global__ void __launch_bounds__(256)
-k_update_matrices(Planes5 R0, Planes5 R1, const float2* __restrict__ flow, int W, int H, Planes5 M)
+k_update_matrices(RView R0, RView R1, const float2* __restrict__ flow, int W, int H, Planes5 M)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     const float2 d = flow[(size_t)y * W + x];
-    const float dx = d.x, dy = d.y;
-    float fx = x + dx, fy = y + dy;
-    int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    fx -= x1; fy -= y1;
-    const size_t o0 = (size_t)y * R0.pitch + x;
-    float r2, r3, r4, r5, r6;
-    if ((unsigned)x1 < (unsigned)(W - 1) && (unsigned)y1 < (unsigned)(H - 1)) {
-        float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const size_t o1 = (size_t)y1 * R1.pitch + x1;
-        const int p = R1.pitch;
-        const float* c;
-        c = R1.ch(0) + o1; r2 = a00 * c[0] + a01 * c[1] + a10 * c[p] + a11 * c[p + 1];
-        c = R1.ch(1) + o1; r3 = a00 * c[0] + a01 * c[1] + a10 * c[p] + a11 * c[p + 1];
-        c = R1.ch(2) + o1; r4 = a00 * c[0] + a01 * c[1] + a10 * c[p] + a11 * c[p + 1];
-        c = R1.ch(3) + o1; r5 = a00 * c[0] + a01 * c[1] + a10 * c[p] + a11 * c[p + 1];
-        c = R1.ch(4) + o1; r6 = a00 * c[0] + a01 * c[1] + a10 * c[p] + a11 * c[p + 1];
-        r4 = (R0.ch(2)[o0] + r4) * 0.5f;
-        r5 = (R0.ch(3)[o0] + r5) * 0.5f;
-        r6 = (R0.ch(4)[o0] + r6) * 0.25f;
-    } else {
-        r2 = r3 = 0.f;
-        r4 = R0.ch(2)[o0]; r5 = R0.ch(3)[o0]; r6 = R0.ch(4)[o0] * 0.5f;
-    }
-    r2 = (R0.ch(0)[o0] - r2) * 0.5f;
-    r3 = (R0.ch(1)[o0] - r3) * 0.5f;
-    r2 += r4 * dy + r6 * dx;
-    r3 += r6 * dy + r5 * dx;
-    if ((unsigned)(x - 5) >= (unsigned)(W - 10) || (unsigned)(y - 5) >= (unsigned)(H - 10)) {
-        const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
-        float scale = (x < 5 ? border[x] : 1.f) * (x >= W - 5 ? border[W - x - 1] : 1.f) *
-                      (y < 5 ? border[y] : 1.f) * (y >= H - 5 ? border[H - y - 1] : 1.f);
-        r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
-    }
+    M5 m = um_pixel(x, y, d.x, d.y, R0, R1, W, H);
     const size_t om = (size_t)y * M.pitch + x;
-    M.ch(0)[om] = r4 * r4 + r6 * r6;
-    M.ch(1)[om] = (r4 + r5) * r6;
-    M.ch(2)[om] = r5 * r5 + r6 * r6;
-    M.ch(3)[om] = r4 * r2 + r6 * r3;
-    M.ch(4)[om] = r6 * r2 + r5 * r3;
+#pragma unroll
+    for (int c = 0; c < 5; c++) M.ch(c)[om] = m.v[c];
+}
+
+__global__ void k_r_interleave(RView src, int W, int H, float* __restrict__ dst)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    size_t o = (size_t)y * src.pitch + x;
+    float4 a = src.a[o];
+    float* d = dst + ((size_t)y * W + x) * 5;
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = src.b[o];
+}
+__global__ void k_r_deinterleave(const float* __restrict__ src, int W, int H, RView dst)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float* s = src + ((size_t)y * W + x) * 5;
+    size_t o = (size_t)y * dst.pitch + x;
+    dst.a[o] = make_float4(s[0], s[1], s[2], s[3]);
+    dst.b[o] = s[4];
 }
 
 __global__ void k_interleave5(Planes5 src, int W, int H, float* __restrict__ dst)
@@ -189,12 +174,23 @@ void launch_scale_flow(Launch& L, float2* flow, size_t n, float mul)
     });
 }
 
-void launch_update_matrices(Launch& L, Planes5 R0, Planes5 R1, const float2* flow, int W, int H, Planes5 M)
+void launch_update_matrices(Launch& L, RView R0, RView R1, const float2* flow, int W, int H, Planes5 M)
 {
     dim3 b(64, 4);
     L.run("update_matrices", [&](cudaStream_t s) {
         k_update_matrices<<<grid2d(W, H, b), b, 0, s>>>(R0, R1, flow, W, H, M);
     });
+}
+
+void launch_r_interleave(Launch& L, RView src, int W, int H, float* dst)
+{
+    dim3 b(64, 4);
+    L.run("r_interleave", [&](cudaStream_t s) { k_r_interleave<<<grid2d(W, H, b), b, 0, s>>>(src, W, H, dst); });
+}
+void launch_r_deinterleave(Launch& L, const float* src, int W, int H, RView dst)
+{
+    dim3 b(64, 4);
+    L.run("r_deinterleave", [&](cudaStream_t s) { k_r_deinterleave<<<grid2d(W, H, b), b, 0, s>>>(src, W, H, dst); });
 }
 
 void launch_interleave5(Launch& L, Planes5 src, int W, int H, float* dst)

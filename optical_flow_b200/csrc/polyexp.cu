@@ -19,19 +19,21 @@ namespace ofb {
 
 struct PolyDev { const float* g; const float* xg; const float* xxg; int n; double ig11, ig03, ig33, ig55; };
 
-__device__ __forceinline__ void polyexp_store(Planes5 R, size_t o, double b1, double b2, double b3, double b4,
+__device__ __forceinline__ void polyexp_store(RView R, size_t o, double b1, double b2, double b3, double b4,
                                               double b5, double b6, const PolyDev& pc)
 {
-    R.ch(1)[o] = (float)(b2 * pc.ig11);
-    R.ch(0)[o] = (float)(b3 * pc.ig11);
-    R.ch(3)[o] = (float)(b1 * pc.ig03 + b4 * pc.ig33);
-    R.ch(2)[o] = (float)(b1 * pc.ig03 + b5 * pc.ig33);
-    R.ch(4)[o] = (float)(b6 * pc.ig55);
+    float4 v;
+    v.y = (float)(b2 * pc.ig11);
+    v.x = (float)(b3 * pc.ig11);
+    v.w = (float)(b1 * pc.ig03 + b4 * pc.ig33);
+    v.z = (float)(b1 * pc.ig03 + b5 * pc.ig33);
+    R.a[o] = v;
+    R.b[o] = (float)(b6 * pc.ig55);
 }
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(256)
-k_polyexp_tiled(const float* __restrict__ I, int W, int H, int pitch, PolyDev pc, Planes5 R)
+k_polyexp_tiled(const float* __restrict__ I, int W, int H, int pitch, PolyDev pc, RView R)
 {
     extern __shared__ float sm[];
     const int n = pc.n, PW = TW + 2 * n, PH = TH + 2 * n;
@@ -111,7 +113,7 @@ k_polyexp_v_generic(const float* __restrict__ I, int W, int H, int pitch, PolyDe
 }
 
 __global__ void __launch_bounds__(256)
-k_polyexp_h_generic(const float* __restrict__ tmp3, size_t plane, int W, int H, int pitch, PolyDev pc, Planes5 R)
+k_polyexp_h_generic(const float* __restrict__ tmp3, size_t plane, int W, int H, int pitch, PolyDev pc, RView R)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -136,7 +138,7 @@ k_polyexp_h_generic(const float* __restrict__ tmp3, size_t plane, int W, int H, 
 }
 
 void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const PolyConst& c,
-                    float* tmp3, Planes5 R, bool generic)
+                    float* tmp3, RView R, bool generic)
 {
     PolyDev pc{c.g, c.xg, c.xxg, c.n, c.ig11, c.ig03, c.ig33, c.ig55};
     constexpr int TW = 64, TH = 16;
@@ -318,21 +320,16 @@ k_polyexp2(PolyArgs a)
         o3[o] = (float)fma(b4[o], a.ig33, b1[o] * a.ig03);
         o4[o] = (float)(b6[o] * a.ig55);
     }
-    const int slot = (a.slot0 + z) % a.R.nslots;
-    float* out = a.R.base + (size_t)slot * a.R.slot_stride + (size_t)gy * a.R.pitch + gx0;
-    const size_t pl = a.R.plane;
+    const RView Rv = a.R.slot(a.R.wrap(a.slot0 + z));
+    const size_t o = (size_t)gy * Rv.pitch + gx0;
     if (gx0 + 3 < W) {
-        *reinterpret_cast<float4*>(out) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-        *reinterpret_cast<float4*>(out + pl) = make_float4(o1[0], o1[1], o1[2], o1[3]);
-        *reinterpret_cast<float4*>(out + 2 * pl) = make_float4(o2[0], o2[1], o2[2], o2[3]);
-        *reinterpret_cast<float4*>(out + 3 * pl) = make_float4(o3[0], o3[1], o3[2], o3[3]);
-        *reinterpret_cast<float4*>(out + 4 * pl) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) Rv.a[o + k] = make_float4(o0[k], o1[k], o2[k], o3[k]);
+        *reinterpret_cast<float4*>(Rv.b + o) = make_float4(o4[0], o4[1], o4[2], o4[3]);
     } else {
 #pragma unroll
-        for (int o = 0; o < 4; o++)
-            if (gx0 + o < W) {
-                out[o] = o0[o]; out[pl + o] = o1[o]; out[2 * pl + o] = o2[o]; out[3 * pl + o] = o3[o]; out[4 * pl + o] = o4[o];
-            }
+        for (int k = 0; k < 4; k++)
+            if (gx0 + k < W) { Rv.a[o + k] = make_float4(o0[k], o1[k], o2[k], o3[k]); Rv.b[o + k] = o4[k]; }
     }
 }
 

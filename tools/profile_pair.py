@@ -13,6 +13,8 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
 H = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
 eng = ofb.Farneback(0)
+if os.environ.get("OFB_BATCH"):
+    eng.set_option("batch", int(os.environ["OFB_BATCH"]))
 frames = synth_frames.shot(W, H, P + 1, seed=5)
 d_frames = eng.device_alloc(frames.nbytes)
 d_bgr = eng.device_alloc(P * W * H * 3)
