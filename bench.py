@@ -214,6 +214,9 @@ def run_ours(args, rank, local_rank, world):
         eng.set_option("batch", args.batch)
     if args.batch_scale0 >= 0:
         eng.set_option("batch_scale0", args.batch_scale0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     try:
         import torch
         torch.cuda.set_device(local_rank)
@@ -357,6 +360,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--ref-pairs-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (experiments)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per launch inside a shot (0 = engine default)")
     ap.add_argument("--batch-scale0", type=int, default=-1, help="pairs per launch at scale 0 (-1 = default, 0 = same as --batch)")
     args = ap.parse_args()

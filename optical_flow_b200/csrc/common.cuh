@@ -65,6 +65,7 @@ struct IterArgs {
     SlotRing R; int slot0;
     float2* flow; size_t flow_item;
     int W, H, strip_rows; float c;          // c = 1e-3 * winsize^4
+    int prefetch;                           // 1 = software-prefetch the next step's lines into L2
 };
 
 // polynomial expansion (polyexp.cu); batch item z = frame
@@ -152,6 +153,8 @@ void launch_deinterleave5(Launch& L, const float* src /* (H,W,5) */, int W, int 
 // iter.cu -- A.8 / A.9 / A.11 batched
 void launch_um0(Launch& L, int src, const Um0Args& a, int batch);
 bool iter_supported(int winsize);
+void set_iter_ilp(int v);
+void set_iter_prefetch(int v);
 void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count);
 
 // blur_solve.cu -- A.9 / A.10

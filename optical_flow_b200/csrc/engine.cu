@@ -88,7 +88,7 @@ struct ofb_context {
     std::string err;
     Profiler prof;
     bool generic = false;
-    int batch = 4;                      // pairs per launch inside a shot
+    int batch = 0;                      // pairs per launch inside a shot (0 = choose from the frame size)
     int batch0 = 0;                     // pairs per launch at scale 0 (0 = same as batch)
     Plan plan;
     unsigned* minmax = nullptr;         // 2 per batch item
@@ -492,6 +492,19 @@ void picture(ofb_context* ctx, Launch& L, const float2* d_flow, size_t flow_item
     launch_picture_batch(L, d_flow, flow_item, n, ctx->minmax, d_bgr, bgr_item, count);
 }
 
+// Pairs per launch inside a shot: enough pixels per launch to fill 148 SMs at the coarse scales and to
+// amortise launch latency, bounded by workspace size (~90 MB of M / R / flow per 1080p pair).
+int shot_batch(const ofb_context* ctx, int W, int H, int n_pairs)
+{
+    int b = ctx->batch;
+    if (b <= 0) {
+        double px = (double)W * H;
+        b = (int)std::ceil(32.0e6 / px);
+        b = std::max(4, std::min(b, MAX_BATCH));
+    }
+    return std::max(1, std::min(b, std::min(n_pairs, MAX_BATCH)));
+}
+
 int no_initial_flow(ofb_context* ctx, const ofb_params* p)
 {
     if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW)
@@ -787,7 +800,7 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
     if (!d_frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
     if (int rc = no_initial_flow(ctx, p)) return rc;
     CU(cudaSetDevice(ctx->device));
-    const int B = std::max(1, std::min(ctx->batch, std::min(n_frames - 1, MAX_BATCH)));
+    const int B = shot_batch(ctx, W, H, n_frames - 1);
     if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t s = ctx->s_compute;
@@ -817,7 +830,7 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
     if (!frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
     if (int rc = no_initial_flow(ctx, p)) return rc;
     CU(cudaSetDevice(ctx->device));
-    const int B = std::max(1, std::min(ctx->batch, std::min(n_frames - 1, MAX_BATCH)));
+    const int B = shot_batch(ctx, W, H, n_frames - 1);
     if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t sc = ctx->s_compute, su = ctx->s_h2d, sd = ctx->s_d2h;
@@ -1060,7 +1073,9 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
 {
     if (!ctx || !name) return OFB_ERR_BAD_ARG;
     if (!strcmp(name, "generic_kernels")) { ctx->generic = value != 0; return OFB_OK; }
-    if (!strcmp(name, "batch")) { ctx->batch = std::max(1, std::min(value, MAX_BATCH)); return OFB_OK; }
+    if (!strcmp(name, "iter_ilp")) { set_iter_ilp(value); return OFB_OK; }
+    if (!strcmp(name, "iter_prefetch")) { set_iter_prefetch(value); return OFB_OK; }
+    if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "profile")) {
         cudaSetDevice(ctx->device);

@@ -88,8 +88,10 @@ __device__ __forceinline__ float kahan_det(float a, float d, float b, float c)  
     return __fadd_rn(f, e);
 }
 
-template <int M, bool FUSE>
-__global__ void __launch_bounds__(IT_THREADS, (M <= 8) ? 2 : 1)
+// ILP = number of pixels whose UpdateMatrices gathers one thread keeps in flight in the S phase.
+// ILP 1 fits two CTAs per SM (<= 68 registers); ILP > 1 trades the second CTA for deeper memory parallelism.
+template <int M, bool FUSE, int ILP>
+__global__ void __launch_bounds__(IT_THREADS, (M <= 8 && ILP == 1) ? 2 : 1)
 k_iter(IterArgs a)
 {
     constexpr int R = 2 * M + 1;
@@ -132,6 +134,45 @@ k_iter(IterArgs a)
         float blkB[R];                                                 // rows ys+M+1 .. ys+3M+1
 #pragma unroll
         for (int r = 0; r < R; r++) blkB[r] = src[(size_t)min(ys + M + 1 + r, H - 1) * pitch];
+        if (a.prefetch) {
+            // Software prefetch into L2, one step (~R rows) ahead: the M rows the next V phase will load and
+            // the R0 / R1 rows the next S phase will read (R1 at the un-displaced position; flow displacements
+            // are small next to a step).  Turns DRAM-latency stalls of the gathers into L2 hits.
+            const int yn = ys + R;                       // first output row of the next step
+            if (yn < yend) {
+                constexpr int LPR_M = (IT_CW * 4 + 127) / 128 + 1;         // 128-byte lines per M row segment
+                constexpr int NM = 5 * R * LPR_M;
+                constexpr int LPR_A = (TW * 16 + 127) / 128 + 1, LPR_B = (TW * 4 + 127) / 128 + 1;
+                constexpr int NR = R * (LPR_A + LPR_B);
+                const int total = NM + (FUSE ? 2 * NR : 0);
+                for (int i = tid; i < total; i += IT_THREADS) {
+                    const char* p;
+                    if (i < NM) {
+                        int c = i / (R * LPR_M), rem = i - c * (R * LPR_M), r = rem / LPR_M, l = rem - r * LPR_M;
+                        int row = min(yn + M + 1 + r, H - 1);
+                        int col = max(x0 - M, 0) + 32 * l;
+                        if (col >= pitch) continue;
+                        p = (const char*)(a.Min + (size_t)z * a.m_item + (size_t)c * a.plane + (size_t)row * pitch + col);
+                    } else {
+                        int j = i - NM;
+                        const RView& Rv = (j < NR) ? R0 : R1;
+                        if (j >= NR) j -= NR;
+                        int r = j / (LPR_A + LPR_B), l = j - r * (LPR_A + LPR_B);
+                        int row = min(yn + r, H - 1);
+                        if (l < LPR_A) {
+                            int col = x0 + 8 * l;
+                            if (col >= pitch) continue;
+                            p = (const char*)(Rv.a + (size_t)row * Rv.pitch + col);
+                        } else {
+                            int col = x0 + 32 * (l - LPR_A);
+                            if (col >= pitch) continue;
+                            p = (const char*)(Rv.b + (size_t)row * Rv.pitch + col);
+                        }
+                    }
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
+            }
+        }
 #pragma unroll
         for (int i = R - 2; i >= 0; i--) blkA[i] = __fadd_rn(blkA[i], blkA[i + 1]);      // suffix sums
         {
@@ -173,24 +214,58 @@ k_iter(IterArgs a)
         __syncthreads();
 
         // ---- S phase: item = pixel ----
-        for (int i = tid; i < R * TW; i += IT_THREADS) {
-            const int r = i / TW, lx = i - r * TW;
-            const int y = ys + r, x = x0 + lx;
-            if (y < yend && x < W) {
-                const float* h = sH + r * HP + lx;
-                const float g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
-                // flow = [g11*h2 - g12*h1, g22*h1 - g12*h2] * scale^2 / ((g11*g22 - g12^2) * scale^2 + 1e-3)
-                //      = [ ... ] / (g11*g22 - g12^2 + 1e-3 / scale^2)
-                const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
-                const float fx = __fdiv_rn(kahan_det(g11, h2, g12, h1), det);
-                const float fy = __fdiv_rn(kahan_det(g22, h1, g12, h2), det);
-                if (FUSE) {
-                    M5 m = um_pixel(x, y, fx, fy, R0, R1, W, H);
-                    float* o = mout + (size_t)y * pitch + x;
+        if (ILP == 1) {
+            for (int i = tid; i < R * TW; i += IT_THREADS) {
+                const int r = i / TW, lx = i - r * TW;
+                const int y = ys + r, x = x0 + lx;
+                if (y < yend && x < W) {
+                    const float* h = sH + r * HP + lx;
+                    const float g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
+                    // flow = [g11*h2 - g12*h1, g22*h1 - g12*h2] * scale^2 / ((g11*g22 - g12^2) * scale^2 + 1e-3)
+                    //      = [ ... ] / (g11*g22 - g12^2 + 1e-3 / scale^2)
+                    const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
+                    const float fx = __fdiv_rn(kahan_det(g11, h2, g12, h1), det);
+                    const float fy = __fdiv_rn(kahan_det(g22, h1, g12, h2), det);
+                    if (FUSE) {
+                        M5 m = um_pixel(x, y, fx, fy, R0, R1, W, H);
+                        float* o = mout + (size_t)y * pitch + x;
 #pragma unroll
-                    for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
-                } else {
-                    fout[(size_t)y * W + x] = make_float2(fx, fy);
+                        for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
+                    } else {
+                        fout[(size_t)y * W + x] = make_float2(fx, fy);
+                    }
+                }
+            }
+        } else {
+            for (int i0 = tid; i0 < R * TW; i0 += ILP * IT_THREADS) {
+                UmLoads L[ILP];
+                bool ok[ILP];
+#pragma unroll
+                for (int j = 0; j < ILP; j++) {
+                    const int i = i0 + j * IT_THREADS;
+                    const int r = i / TW, lx = i - r * TW;
+                    const int y = ys + r, x = x0 + lx;
+                    ok[j] = (i < R * TW) && y < yend && x < W;
+                    if (ok[j]) {
+                        const float* h = sH + r * HP + lx;
+                        const float g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
+                        const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
+                        const float fx = __fdiv_rn(kahan_det(g11, h2, g12, h1), det);
+                        const float fy = __fdiv_rn(kahan_det(g22, h1, g12, h2), det);
+                        if (FUSE) L[j] = um_load(x, y, fx, fy, R0, R1, W, H);
+                        else fout[(size_t)y * W + x] = make_float2(fx, fy);
+                    }
+                }
+                if (FUSE) {
+#pragma unroll
+                    for (int j = 0; j < ILP; j++) {
+                        if (ok[j]) {
+                            M5 m = um_compute(L[j], W, H);
+                            float* o = mout + (size_t)L[j].y * pitch + L[j].x;
+#pragma unroll
+                            for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
+                        }
+                    }
                 }
             }
         }
@@ -199,14 +274,19 @@ k_iter(IterArgs a)
     }
 }
 
-template <int M, bool FUSE>
+static int g_iter_ilp = 1;
+void set_iter_ilp(int v) { g_iter_ilp = v; }
+static int g_iter_prefetch = 1;
+void set_iter_prefetch(int v) { g_iter_prefetch = v; }
+
+template <int M, bool FUSE, int ILP>
 static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
 {
     constexpr int R = 2 * M + 1, TW = IT_CW - 2 * M, HP = TW + 1;
     const size_t smem = sizeof(float) * (5 * R * IT_VP + 5 * R * HP);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_iter<M, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_iter<M, FUSE, ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     const int xt = divup(a.W, TW);
@@ -218,19 +298,27 @@ static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
     strip = std::max(strip, std::min(a.H, 2 * R));          // keep the block-A preload amortised
     strip = divup(strip, R) * R;
     a.strip_rows = strip;
+    a.prefetch = g_iter_prefetch;
     dim3 grid(xt, divup(a.H, strip), batch);
     L.run(FUSE ? "iter_fused" : "iter_last", [&](cudaStream_t s) {
-        k_iter<M, FUSE><<<grid, IT_THREADS, smem, s>>>(a);
+        k_iter<M, FUSE, ILP><<<grid, IT_THREADS, smem, s>>>(a);
     });
 }
 
 bool iter_supported(int winsize) { int m = winsize / 2; return m >= 1 && m <= 16; }
 
+
 void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count)
 {
     const int m = winsize / 2;
     switch (m) {
-#define OFB_CASE(MM) case MM: if (fuse_um) run_iter<MM, true>(L, a, batch, sm_count); else run_iter<MM, false>(L, a, batch, sm_count); return;
+#define OFB_CASE(MM)                                                                         \
+    case MM:                                                                                 \
+        if (!fuse_um) run_iter<MM, false, 1>(L, a, batch, sm_count);                          \
+        else if (g_iter_ilp >= 3) run_iter<MM, true, 3>(L, a, batch, sm_count);               \
+        else if (g_iter_ilp == 2) run_iter<MM, true, 2>(L, a, batch, sm_count);               \
+        else run_iter<MM, true, 1>(L, a, batch, sm_count);                                    \
+        return;
         OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
         OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)
 #undef OFB_CASE

@@ -182,7 +182,7 @@ void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const Po
 // register window for 4 outputs.
 // ------------------------------------------------------------------------------------------------
 template <int N, int SRC>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 k_polyexp2(PolyArgs a)
 {
     constexpr int TW = 64, TH = 16;
@@ -212,11 +212,30 @@ k_polyexp2(PolyArgs a)
         // raw patch: raw[j][i] = frame(reflect101(y0-N-1+j), reflect101(x0-N-1+i))
         float* raw = sI;
         const int ubx = x0 - N - 1, uby = y0 - N - 1;
-        for (int i = tid; i < RAWH * RAWW; i += 256) {
-            int j = i / RAWW, ii = i - j * RAWW;
-            int fy = reflect101(uby + j, H), fx = reflect101(ubx + ii, W);
-            const unsigned char* row = srcb + (size_t)fy * a.src_pitch;
-            raw[i] = (SRC == 1) ? (float)row[fx] : ((const float*)row)[fx];
+        // interior tiles of a u8 frame: no border arithmetic, 4 pixels per load from the 4-byte aligned
+        // superset [x0-8, x0+TW+8) of the needed columns
+        const bool interior = (SRC == 1) && x0 >= 8 && x0 + TW + 8 <= W && uby >= 0 && uby + RAWH <= H &&
+                              ((a.src_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(srcb) & 3) == 0);
+        if (interior) {
+            constexpr int NVEC = (TW + 16) / 4;
+            constexpr int SHIFT = 7 - N;               // raw column c = (column offset inside the superset) - SHIFT
+            for (int i = tid; i < RAWH * NVEC; i += 256) {
+                int j = i / NVEC, v = i - j * NVEC;
+                const uchar4 q = *reinterpret_cast<const uchar4*>(srcb + (size_t)(uby + j) * a.src_pitch + (x0 - 8) + 4 * v);
+                float* dst = raw + j * RAWW + 4 * v - SHIFT;
+                const int c0 = 4 * v - SHIFT;
+                if (c0 >= 0 && c0 < RAWW) dst[0] = (float)q.x;
+                if (c0 + 1 >= 0 && c0 + 1 < RAWW) dst[1] = (float)q.y;
+                if (c0 + 2 >= 0 && c0 + 2 < RAWW) dst[2] = (float)q.z;
+                if (c0 + 3 >= 0 && c0 + 3 < RAWW) dst[3] = (float)q.w;
+            }
+        } else {
+            for (int i = tid; i < RAWH * RAWW; i += 256) {
+                int j = i / RAWW, ii = i - j * RAWW;
+                int fy = reflect101(uby + j, H), fx = reflect101(ubx + ii, W);
+                const unsigned char* row = srcb + (size_t)fy * a.src_pitch;
+                raw[i] = (SRC == 1) ? (float)row[fx] : ((const float*)row)[fx];
+            }
         }
         __syncthreads();
         // row pass at the (replicate-clamped) patch columns
@@ -269,7 +288,10 @@ k_polyexp2(PolyArgs a)
     const int lx0 = xb * 4;
     const int gy = y0 + ly, gx0 = x0 + lx0;
     if (gy >= H || gx0 >= W) return;
-    double b1[4], b2[4], b3[4], b4[4], b5[4], b6[4];
+    // channel order of the outputs: o0 = d/dy (b3), o1 = d/dx (b2), o2 = yy (b1,b5), o3 = xx (b1,b4), o4 = xy (b6).
+    // One source array at a time, results reduced to f32 as soon as they are complete, to keep the register peak low.
+    float o0[4], o1[4], o2[4], o3[4], o4[4];
+    double c1[4];                                       // b1 * ig03, needed by o2 and o3
     {
         double w[4 + 2 * N];
         const double* q = sR0 + ly * RP + lx0;          // element j of the window = patch column lx0 + j
@@ -285,7 +307,19 @@ k_polyexp2(PolyArgs a)
                 s4 = fma(tg, a.xxgd[k], s4);
                 s2 = fma(w[o + N + k] - w[o + N - k], a.xgd[k], s2);
             }
-            b1[o] = s1; b2[o] = s2; b4[o] = s4;
+            c1[o] = s1 * a.ig03;
+            o1[o] = (float)(s2 * a.ig11);
+            o3[o] = (float)fma(s4, a.ig33, c1[o]);
+        }
+        q = sR2 + ly * RP + lx0;
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double s5 = w[o + N] * a.gd[0];
+#pragma unroll
+            for (int k = 1; k <= N; k++) s5 = fma(w[o + N + k] + w[o + N - k], a.gd[k], s5);
+            o2[o] = (float)fma(s5, a.ig33, c1[o]);
         }
         q = sR1 + ly * RP + lx0;
 #pragma unroll
@@ -298,27 +332,9 @@ k_polyexp2(PolyArgs a)
                 s3 = fma(w[o + N + k] + w[o + N - k], a.gd[k], s3);
                 s6 = fma(w[o + N + k] - w[o + N - k], a.xgd[k], s6);
             }
-            b3[o] = s3; b6[o] = s6;
+            o0[o] = (float)(s3 * a.ig11);
+            o4[o] = (float)(s6 * a.ig55);
         }
-        q = sR2 + ly * RP + lx0;
-#pragma unroll
-        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
-#pragma unroll
-        for (int o = 0; o < 4; o++) {
-            double s5 = w[o + N] * a.gd[0];
-#pragma unroll
-            for (int k = 1; k <= N; k++) s5 = fma(w[o + N + k] + w[o + N - k], a.gd[k], s5);
-            b5[o] = s5;
-        }
-    }
-    float o0[4], o1[4], o2[4], o3[4], o4[4];
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-        o0[o] = (float)(b3[o] * a.ig11);
-        o1[o] = (float)(b2[o] * a.ig11);
-        o2[o] = (float)fma(b5[o], a.ig33, b1[o] * a.ig03);
-        o3[o] = (float)fma(b4[o], a.ig33, b1[o] * a.ig03);
-        o4[o] = (float)(b6[o] * a.ig55);
     }
     const RView Rv = a.R.slot(a.R.wrap(a.slot0 + z));
     const size_t o = (size_t)gy * Rv.pitch + gx0;

@@ -306,7 +306,7 @@ def test_batch_size_does_not_change_results(eng):
                 assert np.array_equal(res["flow"], ref["flow"]), (b, b0)
                 assert np.array_equal(res["bgr"], ref["bgr"]), (b, b0)
     finally:
-        eng.set_option("batch", 4)
+        eng.set_option("batch", 0)
         eng.set_option("batch_scale0", 0)
 
 
