@@ -64,6 +64,8 @@ def peaks():
 # clocks during the timed region
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi sampled every 50 ms from before the warm-up; only samples that arrived inside the timed
+    window [t0, t1] are reported (all samples if the window was too short to catch one)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -75,8 +77,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -84,32 +86,42 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lines):
+            sm, mx, reasons, power = [], [], set(), []
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons, power
+
+        inside = [x for x in self.lines if t0 is not None and t0 <= x[0] <= t1 + 0.06]
+        window = "timed region"
+        if not inside:
+            inside, window = self.lines, "whole run (timed region shorter than the sampling period)"
+        sm, mx, reasons, power = parse(inside)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+                "samples": len(sm), "power_w_max": max(power), "window": window}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -237,19 +249,20 @@ def run_ours(args, rank, local_rank, world):
         eng.synchronize(); tsync(); dist.barrier()
 
     # ---- leg 1: device-resident ("value") ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
     eng.reset_kernel_stats()
-    sampler = ClockSampler(local_rank)
     barrier_sync()
-    sampler.start()
     wall0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
         dev_ms += eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
     barrier_sync()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    wall1 = time.perf_counter()
+    wall = wall1 - wall0
+    clocks = sampler.stop(wall0, wall1)
     launches = sum(v[0] for v in eng.kernel_stats().values())
     t_dev = dist.reduce_max(dev_ms)
     t_wall = dist.reduce_max(wall)
@@ -352,7 +365,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=300)

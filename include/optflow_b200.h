@@ -115,6 +115,10 @@ int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtyp
                   const ofb_params* p, uint8_t* bgr, float* magsum, float* flow);
 int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p,
                   uint8_t* bgr, float* magsum, float* flow, float* device_ms);
+/* n_pairs INDEPENDENT pairs (prev[i], next[i]), each (H, W) uint8 tightly packed: the window loop of
+ * optical_flow.py:83-99, whose pairs need not share frames.  Same outputs as ofb_shot_host. */
+int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, int n_pairs, int W, int H,
+                   const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms);
 int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int W, int H, const ofb_params* p,
                     uint8_t* d_bgr, float* d_magsum, float* d_flow, float* device_ms);
 
@@ -134,7 +138,10 @@ int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, in
 /* ---- options and measurement ----------------------------------------------
  * Options (all default 0):
  *   "generic_kernels"  1 = force the simple global-memory kernels (any winsize / poly_n)
- *   "profile"          1 = bracket every kernel launch with CUDA events on the launching stream */
+ *   "profile"          1 = bracket every kernel launch with CUDA events on the launching stream
+ *   "batch"            pairs per launch inside a shot (0 = chosen from the frame size)
+ *   "batch_scale0"     pairs per launch at scale 0 (0 = same as batch)
+ *   "iter_prefetch"    1 (default) = software L2 prefetch in the iteration kernel */
 int ofb_set_option(ofb_context* ctx, const char* name, int value);
 
 typedef struct ofb_kernel_stat {

@@ -40,12 +40,15 @@ struct SlotRing {
     size_t plane;               // pixels per plane (H * pitch)
     int pitch;
     int nslots;
+    int step;                   // slot distance between consecutive batch items: 1 inside a shot (pair z = frames z, z+1),
+                                // 2 for independent pairs (pair z = slots 2z, 2z+1)
     __host__ __device__ RView slot(int s) const
     {
         float* p = base + (size_t)s * slot_stride;
         return RView{reinterpret_cast<float4*>(p), p + 4 * plane, pitch};
     }
     __host__ __device__ int wrap(int s) const { return s >= nslots ? s - nslots : s; }   // s < 2 * nslots
+    __host__ __device__ int first(int slot0, int z) const { return wrap(slot0 + z * step); }
 };
 
 // first UpdateMatrices of a scale (iter.cu k_um0); batch item z
@@ -73,7 +76,7 @@ struct PolyArgs {
     const void* src; size_t src_item;       // bytes between batch items
     size_t src_pitch;                       // bytes between rows
     int W, H;
-    SlotRing R; int slot0;                  // output slot (slot0 + z) % nslots
+    SlotRing R; int slot0;                  // output slot of frame z: (slot0 + z * R.step) % nslots
     float g[9], xg[9], xxg[9];              // taps k = 0..n (f32, as cv2 builds them)
     double gd[9], xgd[9], xxgd[9];          // the same values widened (exact)
     double ig11, ig03, ig33, ig55;

@@ -275,7 +275,7 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
     CU(cudaStreamSynchronize(ctx->s_h2d));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     free_plan(pl);
-    pl.W = W; pl.H = H; pl.dtype = dtype; pl.p = *p; pl.batch = batch; pl.nslots = batch + 1;
+    pl.W = W; pl.H = H; pl.dtype = dtype; pl.p = *p; pl.batch = batch; pl.nslots = 2 * batch;
     pl.K = num_scales(W, H, p->pyr_scale, p->levels);
     pl.lv.resize(pl.K + 1);
     const size_t B = (size_t)batch;
@@ -347,7 +347,7 @@ RView slot_planes(const Level& l, int slot)
     float* p = l.R + (size_t)slot * l.slot_stride();
     return RView{reinterpret_cast<float4*>(p), p + 4 * l.plane(), l.pitch};
 }
-SlotRing ring(const Plan& pl, const Level& l) { return SlotRing{l.R, l.slot_stride(), l.plane(), l.pitch, pl.nslots}; }
+SlotRing ring(const Plan& pl, const Level& l, int step = 1) { return SlotRing{l.R, l.slot_stride(), l.plane(), l.pitch, pl.nslots, step}; }
 Planes5 m_planes(const Plan& pl, const Level& l, int which, int item)
 {
     return Planes5{pl.M[which] + (size_t)item * pl.m_item, l.plane(), l.pitch};
@@ -355,7 +355,8 @@ Planes5 m_planes(const Plan& pl, const Level& l, int which, int item)
 
 // Per-frame part for `count` consecutive frames (first one = frame index f0 of the shot -> slot f0 % nslots).
 // Frames are `item_bytes` apart starting at d_frames, rows `pitch_bytes` apart.
-void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t item_bytes, size_t pitch_bytes, int f0, int count)
+void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t item_bytes, size_t pitch_bytes, int f0, int count,
+                   int slot_step = 1)
 {
     Plan& pl = ctx->plan;
     const bool fast = pl.fast_poly && !ctx->generic;
@@ -365,7 +366,7 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
         if (fast && k == 0) {
             PolyArgs a = pl.pa;
             a.src = d_frames; a.src_item = item_bytes; a.src_pitch = pitch_bytes;
-            a.W = l.W; a.H = l.H; a.R = ring(pl, l); a.slot0 = slot0;
+            a.W = l.W; a.H = l.H; a.R = ring(pl, l, slot_step); a.slot0 = slot0;
             launch_polyexp2(L, pl.dtype == OFB_U8 ? 1 : 2, a, count);
             continue;
         }
@@ -378,7 +379,7 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
             launch_pyr2(L, pl.dtype, py, count);
             PolyArgs a = pl.pa;
             a.src = pl.I; a.src_item = pl.i_item * sizeof(float); a.src_pitch = (size_t)l.pitch * sizeof(float);
-            a.W = l.W; a.H = l.H; a.R = ring(pl, l); a.slot0 = slot0;
+            a.W = l.W; a.H = l.H; a.R = ring(pl, l, slot_step); a.slot0 = slot0;
             launch_polyexp2(L, 0, a, count);
             continue;
         }
@@ -386,14 +387,14 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
             const char* fr = (const char*)d_frames + (size_t)z * item_bytes;
             launch_pyr_h(L, fr, pl.dtype, pl.W, pl.H, pitch_bytes, l.taps, l.ksize, pl.T, l.W, l.pitch);
             launch_pyr_v(L, pl.T, pl.H, l.pitch, l.taps, l.ksize, pl.I, l.W, l.H, l.pitch);
-            launch_polyexp(L, pl.I, l.W, l.H, l.pitch, pl.pc, pl.tmp3, slot_planes(l, (f0 + z) % pl.nslots), ctx->generic);
+            launch_polyexp(L, pl.I, l.W, l.H, l.pitch, pl.pc, pl.tmp3, slot_planes(l, (f0 + z * slot_step) % pl.nslots), ctx->generic);
         }
     }
 }
 
 // Per-pair part for `count` consecutive pairs; pair z uses the slots of frames t0+z and t0+z+1 and writes
 // its scale-0 flow to d_flow + z * flow_item (float2 units).  `initial` = OPTFLOW_USE_INITIAL_FLOW (count == 1).
-void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow, size_t flow_item)
+void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow, size_t flow_item, int step = 1)
 {
     Plan& pl = ctx->plan;
     const ofb_params& p = pl.p;
@@ -414,7 +415,7 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
             for (int z0 = 0; z0 < count; z0 += sub) {
                 const int nb = std::min(sub, count - z0);
                 Um0Args u{};
-                u.R = ring(pl, l); u.slot0 = (slot0 + z0) % pl.nslots;
+                u.R = ring(pl, l, step); u.slot0 = (slot0 + z0 * step) % pl.nslots;
                 u.M = pl.M[0] + (size_t)z0 * pl.m_item; u.m_item = pl.m_item; u.plane = l.plane(); u.pitch = l.pitch;
                 u.W = l.W; u.H = l.H;
                 int src = 0;
@@ -435,7 +436,7 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                     IterArgs a{};
                     a.Min = pl.M[cur] + (size_t)z0 * pl.m_item; a.Mout = pl.M[cur ^ 1] + (size_t)z0 * pl.m_item;
                     a.m_item = pl.m_item; a.plane = l.plane(); a.pitch = l.pitch;
-                    a.R = ring(pl, l); a.slot0 = (slot0 + z0) % pl.nslots;
+                    a.R = ring(pl, l, step); a.slot0 = (slot0 + z0 * step) % pl.nslots;
                     a.flow = flow + (size_t)z0 * fitem; a.flow_item = fitem;
                     a.W = l.W; a.H = l.H; a.c = c4;
                     launch_iter(L, a, p.winsize, !last, nb, ctx->sm_count);
@@ -453,7 +454,7 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                 const Level& cl = pl.lv[k + 1];
                 launch_upsample_flow(L, cl.flow + (size_t)z * cl.flow_item(), cl.W, cl.H, fl, l.W, l.H, up_mul);
             }
-            RView R0 = slot_planes(l, (slot0 + z) % pl.nslots), R1 = slot_planes(l, (slot0 + z + 1) % pl.nslots);
+            RView R0 = slot_planes(l, (slot0 + z * step) % pl.nslots), R1 = slot_planes(l, (slot0 + z * step + 1) % pl.nslots);
             Planes5 M = m_planes(pl, l, 0, 0);
             launch_update_matrices(L, R0, R1, fl, l.W, l.H, M);
             for (int i = 0; i < p.iterations; i++) {
@@ -793,6 +794,43 @@ int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtyp
     return OFB_OK;
 }
 
+int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, int n_pairs, int W, int H,
+                   const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms)
+{
+    if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
+    if (!prev || !next || n_pairs < 1) return fail(ctx, OFB_ERR_BAD_ARG, "need at least one pair");
+    if (int rc = no_initial_flow(ctx, p)) return rc;
+    CU(cudaSetDevice(ctx->device));
+    const int B = shot_batch(ctx, W, H, n_pairs);
+    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
+    Plan& pl = ctx->plan;
+    cudaStream_t s = ctx->s_compute;
+    const size_t n = (size_t)W * H;
+    float* d_sums = nullptr;
+    if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)n_pairs, &d_sums)) return rc;
+    Launch L{s, &ctx->prof};
+    CU(cudaEventRecord(ctx->ev_t0, s));
+    // chunk of b pairs: slots 2z <- prev[z], 2z+1 <- next[z]; one stream, the two staging buffers hold prev / next
+    for (int t0 = 0; t0 < n_pairs; t0 += B) {
+        const int b = std::min(B, n_pairs - t0);
+        CU(cudaMemcpyAsync(pl.fstage[0], prev + (size_t)t0 * n, (size_t)b * n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(pl.fstage[1], next + (size_t)t0 * n, (size_t)b * n, cudaMemcpyHostToDevice, s));
+        expand_frames(ctx, L, pl.fstage[0], n, (size_t)W, 0, b, 2);     // prev[z] -> slot 2z
+        expand_frames(ctx, L, pl.fstage[1], n, (size_t)W, 1, b, 2);     // next[z] -> slot 2z+1
+        solve_pairs(ctx, L, 0, b, pl.flow0[0], n, 2);
+        if (bgr) picture(ctx, L, pl.flow0[0], n, n, pl.bgr[0], n * 3, b);
+        if (magsum) launch_sum_magnitude_batch(L, pl.flow0[0], n, n, ctx->sumacc, d_sums + t0, b);
+        CU(cudaGetLastError());
+        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[0], (size_t)b * n * 3, cudaMemcpyDeviceToHost, s));
+        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[0], (size_t)b * n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (magsum) CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(ctx->ev_t1, s));
+    CU(cudaStreamSynchronize(s));
+    if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
+    return OFB_OK;
+}
+
 int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int W, int H, const ofb_params* p,
                     uint8_t* d_bgr, float* d_magsum, float* d_flow, float* device_ms)
 {
@@ -964,7 +1002,7 @@ int ofb_stage_polyexp(ofb_context* ctx, const float* img, int W, int H, int poly
         PolyArgs a;
         fill_poly_args(a, poly_n, tab, ig);
         a.src = dI; a.src_item = 0; a.src_pitch = sizeof(float) * (size_t)pitch; a.W = W; a.H = H;
-        a.R = SlotRing{dR, 5 * plane, plane, pitch, 1}; a.slot0 = 0;
+        a.R = SlotRing{dR, 5 * plane, plane, pitch, 1, 1}; a.slot0 = 0;
         launch_polyexp2(L, 0, a, 1);
     } else {
         launch_polyexp(L, dI, W, H, pitch, pc, dtmp, Rp, ctx->generic);
@@ -1002,7 +1040,7 @@ int ofb_stage_update_matrices(ofb_context* ctx, const float* R0, const float* R1
     } else {
         Um0Args u{};
         u.flow = (const float2*)dfl; u.flow_item = 0;
-        u.R = SlotRing{dR, 5 * plane, plane, pitch, 2}; u.slot0 = 0;
+        u.R = SlotRing{dR, 5 * plane, plane, pitch, 2, 1}; u.slot0 = 0;
         u.M = dM; u.m_item = 0; u.plane = plane; u.pitch = pitch; u.W = W; u.H = H;
         launch_um0(L, 1, u, 1);
     }

@@ -55,7 +55,7 @@ k_um0(Um0Args a)
         dx = (hx0 * b0 + hx1 * b1) * a.mul;
         dy = (hy0 * b0 + hy1 * b1) * a.mul;
     }
-    const int s0 = a.R.wrap(a.slot0 + z), s1 = a.R.wrap(s0 + 1);
+    const int s0 = a.R.first(a.slot0, z), s1 = a.R.wrap(s0 + 1);
     M5 m = um_pixel(x, y, dx, dy, a.R.slot(s0), a.R.slot(s1), a.W, a.H);
     float* out = a.M + (size_t)z * a.m_item + (size_t)y * a.pitch + x;
 #pragma unroll
@@ -122,7 +122,7 @@ k_iter(IterArgs a)
     float* mout = nullptr;
     float2* fout = nullptr;
     if (FUSE) {
-        const int s0 = a.R.wrap(a.slot0 + z), s1 = a.R.wrap(s0 + 1);
+        const int s0 = a.R.first(a.slot0, z), s1 = a.R.wrap(s0 + 1);
         R0 = a.R.slot(s0); R1 = a.R.slot(s1);
         mout = a.Mout + (size_t)z * a.m_item;
     } else {

@@ -336,7 +336,7 @@ k_polyexp2(PolyArgs a)
             o4[o] = (float)(s6 * a.ig55);
         }
     }
-    const RView Rv = a.R.slot(a.R.wrap(a.slot0 + z));
+    const RView Rv = a.R.slot(a.R.first(a.slot0, z));
     const size_t o = (size_t)gy * Rv.pitch + gx0;
     if (gx0 + 3 < W) {
 #pragma unroll

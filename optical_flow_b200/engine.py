@@ -224,6 +224,23 @@ class Farneback:
                                           C.byref(dev_ms)))
         return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
 
+    def pairs(self, prev_frames, next_frames, want_bgr=False, want_magsum=True, want_flow=False, **params):
+        """n independent pairs (prev_frames[i], next_frames[i]) in one batched submission: the window loop of
+        optical_flow.py:83-99 (its pairs need not share frames)."""
+        a = np.ascontiguousarray(prev_frames)
+        b = np.ascontiguousarray(next_frames)
+        if a.shape != b.shape or a.ndim != 3 or a.dtype != np.uint8 or b.dtype != np.uint8 or a.shape[0] < 1:
+            raise ValueError("prev_frames / next_frames must both be (n>=1, H, W) uint8")
+        n, H, W = a.shape
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        bgr = np.empty((n, H, W, 3), np.uint8) if want_bgr else None
+        ms = np.zeros(n, np.float32) if want_magsum else None
+        fl = np.empty((n, H, W, 2), np.float32) if want_flow else None
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_pairs_host(self._h, _ptr(a), _ptr(b), n, W, H, C.byref(prm), _ptr(bgr), _ptr(ms), _ptr(fl),
+                                           C.byref(dev_ms)))
+        return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
+
     # -- device-resident shot (bench: inputs already in HBM) -------------------------------------------
     def device_alloc(self, nbytes):
         p = self._L.ofb_device_alloc(self._h, int(nbytes))
