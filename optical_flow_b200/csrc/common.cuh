@@ -69,6 +69,9 @@ struct IterArgs {
     float2* flow; size_t flow_item;
     int W, H, strip_rows; float c;          // c = 1e-3 * winsize^4
     int prefetch;                           // 1 = software-prefetch the next step's lines into L2
+    unsigned* minmax;                       // non-null (FUSE = false only): fold min / max of |flow| of item z into minmax[2z..]
+    int gauss;                              // 1 = Gaussian window (flags & 256): taps gk[0..M], c = 1e-3
+    float gk[17];
 };
 
 // polynomial expansion (polyexp.cu); batch item z = frame
@@ -109,6 +112,11 @@ __host__ __device__ inline int reflect101(int p, int len)
     }
     return p;
 }
+
+// u8 -> f32 without an I2F (which runs on the 16-lane XU pipe): place the byte in the mantissa of 2^23.
+__device__ __forceinline__ float u8_to_f32(unsigned int b) { return __uint_as_float(0x4B000000u | b) - 8388608.f; }
+template <typename T> __device__ __forceinline__ float px_to_f32(T v) { return (float)v; }
+template <> __device__ __forceinline__ float px_to_f32<unsigned char>(unsigned char v) { return u8_to_f32(v); }
 
 // Source coordinate of cv::resize(INTER_LINEAR), evaluated in double like the
 // installed wheel does: returns the left/top sample index, writes the f32 weight of the next one.
@@ -170,7 +178,8 @@ void launch_blur_solve_gauss(Launch& L, Planes5 M, int W, int H, int winsize, co
 // viz.cu -- Appendix B
 // batched over pairs: flow / bgr / minmax / sums advance by *_item per batch element
 void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax /* 2 per item */,
-                          uint8_t* bgr, size_t bgr_item, int batch);
+                          uint8_t* bgr, size_t bgr_item, int batch, bool minmax_done = false);
+void launch_minmax_reset_batch(Launch& L, unsigned* minmax, int batch);
 void launch_sum_magnitude_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, double* acc /* 1 per item */,
                                 float* out /* 1 per item */, int batch);
 void launch_minmax_mag(Launch& L, const float2* flow, size_t n, unsigned* minmax /* [2], pre-set */);

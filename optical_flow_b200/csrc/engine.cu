@@ -76,6 +76,7 @@ struct Plan {
     size_t sums_cap = 0;
     std::vector<void*> allocs;
     bool fast_poly = false, fast_iter = false;
+    std::vector<float> gk;              // host copy of the Gaussian window half taps
 };
 
 }  // namespace
@@ -337,7 +338,8 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
         if (int rc = dalloc(ctx, pl, &pl.bgr[s], B * n * 3)) return rc;
     }
     pl.fast_poly = polyexp2_supported(p->poly_n);
-    pl.fast_iter = !(p->flags & OFB_OPTFLOW_FARNEBACK_GAUSSIAN) && iter_supported(p->winsize) && p->iterations >= 1;
+    pl.fast_iter = iter_supported(p->winsize) && p->iterations >= 1;
+    pl.gk = gk;
     pl.valid = true;
     return 0;
 }
@@ -394,7 +396,8 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
 
 // Per-pair part for `count` consecutive pairs; pair z uses the slots of frames t0+z and t0+z+1 and writes
 // its scale-0 flow to d_flow + z * flow_item (float2 units).  `initial` = OPTFLOW_USE_INITIAL_FLOW (count == 1).
-void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow, size_t flow_item, int step = 1)
+bool solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow, size_t flow_item, int step = 1,
+                 bool want_minmax = false)
 {
     Plan& pl = ctx->plan;
     const ofb_params& p = pl.p;
@@ -403,6 +406,8 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
     const bool fast = pl.fast_iter && !ctx->generic;
     const float c4 = (float)(1e-3 * (double)p.winsize * p.winsize * p.winsize * p.winsize);
     const float up_mul = (float)(1. / p.pyr_scale);
+    const bool fold_minmax = want_minmax && fast;          // min / max of |flow| folded into the last launch of scale 0
+    if (fold_minmax) launch_minmax_reset_batch(L, ctx->minmax, count);
     for (int k = pl.K; k >= 0; k--) {
         Level& l = pl.lv[k];
         float2* flow = k == 0 ? d_flow : l.flow;
@@ -438,7 +443,10 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                     a.m_item = pl.m_item; a.plane = l.plane(); a.pitch = l.pitch;
                     a.R = ring(pl, l, step); a.slot0 = (slot0 + z0 * step) % pl.nslots;
                     a.flow = flow + (size_t)z0 * fitem; a.flow_item = fitem;
-                    a.W = l.W; a.H = l.H; a.c = c4;
+                    a.W = l.W; a.H = l.H; a.c = gaussian ? 1e-3f : c4;
+                    a.gauss = gaussian ? 1 : 0;
+                    if (gaussian) for (size_t q = 0; q < pl.gk.size() && q < 17; q++) a.gk[q] = pl.gk[q];
+                    a.minmax = (fold_minmax && last && k == 0) ? ctx->minmax + 2 * z0 : nullptr;
                     launch_iter(L, a, p.winsize, !last, nb, ctx->sm_count);
                     cur ^= 1;
                 }
@@ -464,8 +472,8 @@ void solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
             }
         }
     }
+    return fold_minmax;
 }
-
 
 int stage_buf(ofb_context* ctx, int i, size_t bytes, float** out)
 {
@@ -488,9 +496,10 @@ int upload_frame(ofb_context* ctx, const void* src, size_t pitch, int W, int H, 
     return 0;
 }
 
-void picture(ofb_context* ctx, Launch& L, const float2* d_flow, size_t flow_item, size_t n, uint8_t* d_bgr, size_t bgr_item, int count)
+void picture(ofb_context* ctx, Launch& L, const float2* d_flow, size_t flow_item, size_t n, uint8_t* d_bgr, size_t bgr_item, int count,
+             bool minmax_done = false)
 {
-    launch_picture_batch(L, d_flow, flow_item, n, ctx->minmax, d_bgr, bgr_item, count);
+    launch_picture_batch(L, d_flow, flow_item, n, ctx->minmax, d_bgr, bgr_item, count, minmax_done);
 }
 
 // Pairs per launch inside a shot: enough pixels per launch to fill 148 SMs at the coarse scales and to
@@ -783,8 +792,8 @@ int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtyp
     Launch L{s, &ctx->prof};
     expand_frames(ctx, L, pl.f0, 0, row, 0, 1);
     expand_frames(ctx, L, pl.fstage[0], 0, row, 1, 1);
-    solve_pairs(ctx, L, 0, 1, pl.flow0[0], n);
-    if (bgr) picture(ctx, L, pl.flow0[0], 0, n, pl.bgr[0], 0, 1);
+    const bool mm = solve_pairs(ctx, L, 0, 1, pl.flow0[0], n, 1, bgr != nullptr);
+    if (bgr) picture(ctx, L, pl.flow0[0], 0, n, pl.bgr[0], 0, 1, mm);
     if (magsum) launch_sum_magnitude_batch(L, pl.flow0[0], 0, n, ctx->sumacc, ctx->sumout, 1);
     CU(cudaGetLastError());
     if (bgr) CU(cudaMemcpyAsync(bgr, pl.bgr[0], n * 3, cudaMemcpyDeviceToHost, s));
@@ -817,8 +826,8 @@ int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, i
         CU(cudaMemcpyAsync(pl.fstage[1], next + (size_t)t0 * n, (size_t)b * n, cudaMemcpyHostToDevice, s));
         expand_frames(ctx, L, pl.fstage[0], n, (size_t)W, 0, b, 2);     // prev[z] -> slot 2z
         expand_frames(ctx, L, pl.fstage[1], n, (size_t)W, 1, b, 2);     // next[z] -> slot 2z+1
-        solve_pairs(ctx, L, 0, b, pl.flow0[0], n, 2);
-        if (bgr) picture(ctx, L, pl.flow0[0], n, n, pl.bgr[0], n * 3, b);
+        const bool mm = solve_pairs(ctx, L, 0, b, pl.flow0[0], n, 2, bgr != nullptr);
+        if (bgr) picture(ctx, L, pl.flow0[0], n, n, pl.bgr[0], n * 3, b, mm);
         if (magsum) launch_sum_magnitude_batch(L, pl.flow0[0], n, n, ctx->sumacc, d_sums + t0, b);
         CU(cudaGetLastError());
         if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[0], (size_t)b * n * 3, cudaMemcpyDeviceToHost, s));
@@ -850,8 +859,8 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
         const int b = std::min(B, n_frames - 1 - t0);
         expand_frames(ctx, L, d_frames + (size_t)(t0 + 1) * n, n, (size_t)W, t0 + 1, b);
         float2* fl = d_flow ? (float2*)d_flow + (size_t)t0 * n : pl.flow0[0];
-        solve_pairs(ctx, L, t0, b, fl, n);
-        if (d_bgr) picture(ctx, L, fl, n, n, d_bgr + (size_t)t0 * n * 3, n * 3, b);
+        const bool mm = solve_pairs(ctx, L, t0, b, fl, n, 1, d_bgr != nullptr);
+        if (d_bgr) picture(ctx, L, fl, n, n, d_bgr + (size_t)t0 * n * 3, n * 3, b, mm);
         if (d_magsum) launch_sum_magnitude_batch(L, fl, n, n, ctx->sumacc, d_magsum + t0, b);
     }
     CU(cudaEventRecord(ctx->ev_t1, s));
@@ -900,8 +909,8 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
         expand_frames(ctx, L, pl.fstage[par], n, (size_t)W, t0 + 1, b);
         CU(cudaEventRecord(ctx->ev_frame_free[par], sc));
         if (c >= 2) CU(cudaStreamWaitEvent(sc, ctx->ev_out_free[par], 0));
-        solve_pairs(ctx, L, t0, b, pl.flow0[par], n);
-        if (bgr) picture(ctx, L, pl.flow0[par], n, n, pl.bgr[par], n * 3, b);
+        const bool mm = solve_pairs(ctx, L, t0, b, pl.flow0[par], n, 1, bgr != nullptr);
+        if (bgr) picture(ctx, L, pl.flow0[par], n, n, pl.bgr[par], n * 3, b, mm);
         if (magsum) launch_sum_magnitude_batch(L, pl.flow0[par], n, n, ctx->sumacc, d_sums + t0, b);
         CU(cudaEventRecord(ctx->ev_out_ready[par], sc));
         CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
@@ -1072,14 +1081,16 @@ int ofb_stage_blur_solve(ofb_context* ctx, const float* M, int W, int H, int win
     CU(cudaMemcpyAsync(din, M, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
     launch_deinterleave5(L, din, W, H, pm);
-    if (gaussian) {
-        launch_blur_solve_gauss(L, pm, W, H, winsize, dk, dtmp, (float2*)dfl, true);
-    } else if (!ctx->generic && iter_supported(winsize)) {
+    if (!ctx->generic && iter_supported(winsize)) {
         IterArgs a{};
         a.Min = dM; a.Mout = nullptr; a.m_item = 0; a.plane = plane; a.pitch = pitch;
         a.flow = (float2*)dfl; a.flow_item = 0; a.W = W; a.H = H;
-        a.c = (float)(1e-3 * (double)winsize * winsize * winsize * winsize);
+        a.c = gaussian ? 1e-3f : (float)(1e-3 * (double)winsize * winsize * winsize * winsize);
+        a.gauss = gaussian ? 1 : 0;
+        if (gaussian) for (size_t q = 0; q < gk.size() && q < 17; q++) a.gk[q] = gk[q];
         launch_iter(L, a, winsize, false, 1, ctx->sm_count);
+    } else if (gaussian) {
+        launch_blur_solve_gauss(L, pm, W, H, winsize, dk, dtmp, (float2*)dfl, true);
     } else {
         launch_blur_solve_box(L, pm, W, H, winsize, (double*)dtmp, (float2*)dfl, true);
     }

@@ -90,7 +90,10 @@ __device__ __forceinline__ float kahan_det(float a, float d, float b, float c)  
 
 // ILP = number of pixels whose UpdateMatrices gathers one thread keeps in flight in the S phase.
 // ILP 1 fits two CTAs per SM (<= 68 registers); ILP > 1 trades the second CTA for deeper memory parallelism.
-template <int M, bool FUSE, int ILP>
+// GAUSS = FarnebackUpdateFlow_GaussianBlur (flags & 256): the same strip walk, but the window is a
+// separable Gaussian applied tap by tap in cv2's folded order (k0*c + sum k_i*(a_{+i} + a_{-i}), f32, uncontracted),
+// so the blurred field is bit-identical to cv2's; only the solve differs (compensated f32 instead of f64).
+template <int M, bool FUSE, int ILP, bool GAUSS>
 __global__ void __launch_bounds__(IT_THREADS, (M <= 8 && ILP == 1) ? 2 : 1)
 k_iter(IterArgs a)
 {
@@ -128,6 +131,8 @@ k_iter(IterArgs a)
     } else {
         fout = a.flow + (size_t)z * a.flow_item;
     }
+
+    float mag_lo = __int_as_float(0x7f800000), mag_hi = 0.f;      // per-thread min / max of |flow| (a.minmax)
 
     for (int ys = ybeg; ys < yend; ys += R) {
         // ---- V phase ----
@@ -173,9 +178,25 @@ k_iter(IterArgs a)
                 }
             }
         }
+        if (GAUSS) {
+            float* v = sV + vc * R * IT_VP + vcol;
 #pragma unroll
-        for (int i = R - 2; i >= 0; i--) blkA[i] = __fadd_rn(blkA[i], blkA[i + 1]);      // suffix sums
-        {
+            for (int r = 0; r < R; r++) {
+                // window rows r .. r+2M of the concatenation [blkA | blkB]; centre at r+M
+                const int cidx = r + M;
+                float s0 = (cidx < R ? blkA[cidx] : blkB[cidx - R]) * a.gk[0];
+#pragma unroll
+                for (int i = 1; i <= M; i++) {
+                    const int dn = cidx + i, up = cidx - i;
+                    const float vdn = dn < R ? blkA[dn] : blkB[dn - R];
+                    const float vup = up < R ? blkA[up] : blkB[up - R];
+                    s0 = s0 + (vdn + vup) * a.gk[i];
+                }
+                v[r * IT_VP] = s0;
+            }
+        } else {
+#pragma unroll
+            for (int i = R - 2; i >= 0; i--) blkA[i] = __fadd_rn(blkA[i], blkA[i + 1]);      // suffix sums
             float* v = sV + vc * R * IT_VP + vcol;
             v[0] = blkA[0];
             float p = blkB[0];
@@ -195,19 +216,34 @@ k_iter(IterArgs a)
             const int xa = seg * R;
             const float* v = sV + rc * IT_VP + xa;
             float* h = sH + rc * HP + xa;
-            float sa[R];
+            if (GAUSS) {
+                float w[2 * R - 1];
 #pragma unroll
-            for (int i = 0; i < R; i++) sa[i] = (xa + i < IT_CW) ? v[i] : 0.f;
+                for (int i = 0; i < 2 * R - 1; i++) w[i] = (xa + i < IT_CW) ? v[i] : 0.f;
 #pragma unroll
-            for (int i = R - 2; i >= 0; i--) sa[i] = __fadd_rn(sa[i], sa[i + 1]);
-            if (xa < TW) h[0] = sa[0];
-            float p = 0.f;
+                for (int j = 0; j < R; j++) {
+                    if (xa + j < TW) {
+                        float sum = w[j + M] * a.gk[0];
 #pragma unroll
-            for (int r = 1; r < R; r++) {
-                if (xa + r < TW) {
-                    float nb = v[R + r - 1];                           // column xa+r+2M <= CW-1
-                    p = (r == 1) ? nb : __fadd_rn(p, nb);
-                    h[r] = __fadd_rn(sa[r], p);
+                        for (int i = 1; i <= M; i++) sum = sum + a.gk[i] * (w[j + M - i] + w[j + M + i]);
+                        h[j] = sum;
+                    }
+                }
+            } else {
+                float sa[R];
+#pragma unroll
+                for (int i = 0; i < R; i++) sa[i] = (xa + i < IT_CW) ? v[i] : 0.f;
+#pragma unroll
+                for (int i = R - 2; i >= 0; i--) sa[i] = __fadd_rn(sa[i], sa[i + 1]);
+                if (xa < TW) h[0] = sa[0];
+                float p = 0.f;
+#pragma unroll
+                for (int r = 1; r < R; r++) {
+                    if (xa + r < TW) {
+                        float nb = v[R + r - 1];                           // column xa+r+2M <= CW-1
+                        p = (r == 1) ? nb : __fadd_rn(p, nb);
+                        h[r] = __fadd_rn(sa[r], p);
+                    }
                 }
             }
         }
@@ -233,6 +269,10 @@ k_iter(IterArgs a)
                         for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
                     } else {
                         fout[(size_t)y * W + x] = make_float2(fx, fy);
+                        if (a.minmax) {                        // cv::cartToPolar's magnitude, as in viz.cu
+                            const float mg = sqrtf(fmaf(fx, fx, fy * fy));
+                            mag_lo = fminf(mag_lo, mg); mag_hi = fmaxf(mag_hi, mg);
+                        }
                     }
                 }
             }
@@ -272,6 +312,17 @@ k_iter(IterArgs a)
         // no barrier here: the next V phase writes only sV (last read before the barrier above); sH is
         // next written after the barrier that follows that V phase.
     }
+    if (!FUSE && a.minmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mag_lo = fminf(mag_lo, __shfl_xor_sync(0xffffffffu, mag_lo, o));
+            mag_hi = fmaxf(mag_hi, __shfl_xor_sync(0xffffffffu, mag_hi, o));
+        }
+        if ((tid & 31) == 0) {                                 // magnitudes are >= 0: their bit patterns order like integers
+            atomicMin(a.minmax + 2 * z, __float_as_uint(mag_lo));
+            atomicMax(a.minmax + 2 * z + 1, __float_as_uint(mag_hi));
+        }
+    }
 }
 
 static int g_iter_ilp = 1;
@@ -279,14 +330,14 @@ void set_iter_ilp(int v) { g_iter_ilp = v; }
 static int g_iter_prefetch = 1;
 void set_iter_prefetch(int v) { g_iter_prefetch = v; }
 
-template <int M, bool FUSE, int ILP>
+template <int M, bool FUSE, int ILP, bool GAUSS>
 static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
 {
     constexpr int R = 2 * M + 1, TW = IT_CW - 2 * M, HP = TW + 1;
     const size_t smem = sizeof(float) * (5 * R * IT_VP + 5 * R * HP);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_iter<M, FUSE, ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_iter<M, FUSE, ILP, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     const int xt = divup(a.W, TW);
@@ -300,8 +351,8 @@ static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
     a.strip_rows = strip;
     a.prefetch = g_iter_prefetch;
     dim3 grid(xt, divup(a.H, strip), batch);
-    L.run(FUSE ? "iter_fused" : "iter_last", [&](cudaStream_t s) {
-        k_iter<M, FUSE, ILP><<<grid, IT_THREADS, smem, s>>>(a);
+    L.run(GAUSS ? (FUSE ? "iter_fused_gauss" : "iter_last_gauss") : (FUSE ? "iter_fused" : "iter_last"), [&](cudaStream_t s) {
+        k_iter<M, FUSE, ILP, GAUSS><<<grid, IT_THREADS, smem, s>>>(a);
     });
 }
 
@@ -311,13 +362,26 @@ bool iter_supported(int winsize) { int m = winsize / 2; return m >= 1 && m <= 16
 void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count)
 {
     const int m = winsize / 2;
+    if (a.gauss) {
+        switch (m) {
+#define OFB_CASE(MM)                                                                          \
+    case MM:                                                                                  \
+        if (!fuse_um) run_iter<MM, false, 1, true>(L, a, batch, sm_count);                    \
+        else run_iter<MM, true, 1, true>(L, a, batch, sm_count);                              \
+        return;
+            OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
+            OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)
+#undef OFB_CASE
+            default: return;
+        }
+    }
     switch (m) {
-#define OFB_CASE(MM)                                                                         \
-    case MM:                                                                                 \
-        if (!fuse_um) run_iter<MM, false, 1>(L, a, batch, sm_count);                          \
-        else if (g_iter_ilp >= 3) run_iter<MM, true, 3>(L, a, batch, sm_count);               \
-        else if (g_iter_ilp == 2) run_iter<MM, true, 2>(L, a, batch, sm_count);               \
-        else run_iter<MM, true, 1>(L, a, batch, sm_count);                                    \
+#define OFB_CASE(MM)                                                                          \
+    case MM:                                                                                  \
+        if (!fuse_um) run_iter<MM, false, 1, false>(L, a, batch, sm_count);                   \
+        else if (g_iter_ilp >= 3) run_iter<MM, true, 3, false>(L, a, batch, sm_count);        \
+        else if (g_iter_ilp == 2) run_iter<MM, true, 2, false>(L, a, batch, sm_count);        \
+        else run_iter<MM, true, 1, false>(L, a, batch, sm_count);                             \
         return;
         OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
         OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)

@@ -224,17 +224,17 @@ k_polyexp2(PolyArgs a)
                 const uchar4 q = *reinterpret_cast<const uchar4*>(srcb + (size_t)(uby + j) * a.src_pitch + (x0 - 8) + 4 * v);
                 float* dst = raw + j * RAWW + 4 * v - SHIFT;
                 const int c0 = 4 * v - SHIFT;
-                if (c0 >= 0 && c0 < RAWW) dst[0] = (float)q.x;
-                if (c0 + 1 >= 0 && c0 + 1 < RAWW) dst[1] = (float)q.y;
-                if (c0 + 2 >= 0 && c0 + 2 < RAWW) dst[2] = (float)q.z;
-                if (c0 + 3 >= 0 && c0 + 3 < RAWW) dst[3] = (float)q.w;
+                if (c0 >= 0 && c0 < RAWW) dst[0] = u8_to_f32(q.x);
+                if (c0 + 1 >= 0 && c0 + 1 < RAWW) dst[1] = u8_to_f32(q.y);
+                if (c0 + 2 >= 0 && c0 + 2 < RAWW) dst[2] = u8_to_f32(q.z);
+                if (c0 + 3 >= 0 && c0 + 3 < RAWW) dst[3] = u8_to_f32(q.w);
             }
         } else {
             for (int i = tid; i < RAWH * RAWW; i += 256) {
                 int j = i / RAWW, ii = i - j * RAWW;
                 int fy = reflect101(uby + j, H), fx = reflect101(ubx + ii, W);
                 const unsigned char* row = srcb + (size_t)fy * a.src_pitch;
-                raw[i] = (SRC == 1) ? (float)row[fx] : ((const float*)row)[fx];
+                raw[i] = (SRC == 1) ? u8_to_f32(row[fx]) : ((const float*)row)[fx];
             }
         }
         __syncthreads();

@@ -121,23 +121,23 @@ k_pyr_h2(PyrArgs a)
     if (sx - c >= 0 && sx + 1 + c < W) {
         const T* p = row + sx - c;
         if (a1 != 0.f) {
-            float prev = (float)p[0];
+            float prev = px_to_f32(p[0]);
             for (int j = 0; j < ksize; j++) {
-                float cur = (float)p[j + 1];
+                float cur = px_to_f32(p[j + 1]);
                 float t = __ldg(taps + j);
                 b0 += t * prev;
                 b1 += t * cur;
                 prev = cur;
             }
         } else {
-            for (int j = 0; j < ksize; j++) b0 += __ldg(taps + j) * (float)p[j];
+            for (int j = 0; j < ksize; j++) b0 += __ldg(taps + j) * px_to_f32(p[j]);
         }
     } else {
         int sx1 = min(sx + 1, W - 1);
         for (int j = 0; j < ksize; j++) {
             float t = __ldg(taps + j);
-            b0 += t * (float)row[reflect101(sx + j - c, W)];
-            if (a1 != 0.f) b1 += t * (float)row[reflect101(sx1 + j - c, W)];
+            b0 += t * px_to_f32(row[reflect101(sx + j - c, W)]);
+            if (a1 != 0.f) b1 += t * px_to_f32(row[reflect101(sx1 + j - c, W)]);
         }
     }
     a.T[(size_t)z * a.t_item + (size_t)r * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;

@@ -238,12 +238,19 @@ void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned*
     }
 }
 
-void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax,
-                          uint8_t* bgr, size_t bgr_item, int batch)
+void launch_minmax_reset_batch(Launch& L, unsigned* minmax, int batch)
 {
     L.run("minmax_reset", [&](cudaStream_t s) { k_minmax_reset_batch<<<divup(batch, 64), 64, 0, s>>>(minmax, batch); });
-    dim3 g1(reduce_grid(n, 8), batch);
-    L.run("minmax_mag", [&](cudaStream_t s) { k_minmax_mag<<<g1, 256, 0, s>>>(flow, n, minmax, flow_item); });
+}
+
+void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax,
+                          uint8_t* bgr, size_t bgr_item, int batch, bool minmax_done)
+{
+    if (!minmax_done) {
+        launch_minmax_reset_batch(L, minmax, batch);
+        dim3 g1(reduce_grid(n, 8), batch);
+        L.run("minmax_mag", [&](cudaStream_t s) { k_minmax_mag<<<g1, 256, 0, s>>>(flow, n, minmax, flow_item); });
+    }
     bool vec = (n % 4 == 0) && ((uintptr_t)flow % 16 == 0) && ((uintptr_t)bgr % 4 == 0) && (flow_item % 2 == 0) && (bgr_item % 4 == 0);
     if (vec) {
         size_t n4 = n / 4;
