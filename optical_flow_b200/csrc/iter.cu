@@ -14,7 +14,7 @@
 //            and prefix sums of the new one (van Herk / Gil-Werman): 3 FADD per row, no re-read of M.
 //   H phase  thread = (channel, row, segment of R outputs): the same trick along x out of shared memory.
 //   S phase  thread = pixel: determinant and numerators by Kahan's FMA-compensated a*d-b*c in f32
-//            (error <= 1.5 ulp of the exact f32-input result), one IEEE division each, then (FUSE) the
+//            (error <= 1.5 ulp of the exact f32-input result), one IEEE reciprocal (cv2: idet = 1/det), then (FUSE) the
 //            per-pixel UpdateMatrices with its bilinear gather of R1.
 // Precision: cv2 keeps f64 running sums and an f64 solve.  Here every window sum is a <= 2R-term f32 sum
 // (no running sum over the image, so no drift) and the solve is compensated; measured endpoint difference
@@ -137,8 +137,14 @@ k_iter(IterArgs a)
     for (int ys = ybeg; ys < yend; ys += R) {
         // ---- V phase ----
         float blkB[R];                                                 // rows ys+M+1 .. ys+3M+1
+        if (ys + 3 * M + 1 < H) {                                      // block-uniform: no row of the block is clamped
+            const float* pb = src + (size_t)(ys + M + 1) * pitch;
 #pragma unroll
-        for (int r = 0; r < R; r++) blkB[r] = src[(size_t)min(ys + M + 1 + r, H - 1) * pitch];
+            for (int r = 0; r < R; r++) blkB[r] = pb[r * pitch];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) blkB[r] = src[(size_t)min(ys + M + 1 + r, H - 1) * pitch];
+        }
         if (a.prefetch) {
             // Software prefetch into L2, one step (~R rows) ahead: the M rows the next V phase will load and
             // the R0 / R1 rows the next S phase will read (R1 at the un-displaced position; flow displacements
@@ -260,8 +266,9 @@ k_iter(IterArgs a)
                     // flow = [g11*h2 - g12*h1, g22*h1 - g12*h2] * scale^2 / ((g11*g22 - g12^2) * scale^2 + 1e-3)
                     //      = [ ... ] / (g11*g22 - g12^2 + 1e-3 / scale^2)
                     const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
-                    const float fx = __fdiv_rn(kahan_det(g11, h2, g12, h1), det);
-                    const float fy = __fdiv_rn(kahan_det(g22, h1, g12, h2), det);
+                    const float idet = __frcp_rn(det);
+                    const float fx = __fmul_rn(kahan_det(g11, h2, g12, h1), idet);
+                    const float fy = __fmul_rn(kahan_det(g22, h1, g12, h2), idet);
                     if (FUSE) {
                         M5 m = um_pixel(x, y, fx, fy, R0, R1, W, H);
                         float* o = mout + (size_t)y * pitch + x;
@@ -290,8 +297,9 @@ k_iter(IterArgs a)
                         const float* h = sH + r * HP + lx;
                         const float g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
                         const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
-                        const float fx = __fdiv_rn(kahan_det(g11, h2, g12, h1), det);
-                        const float fy = __fdiv_rn(kahan_det(g22, h1, g12, h2), det);
+                        const float idet = __frcp_rn(det);
+                        const float fx = __fmul_rn(kahan_det(g11, h2, g12, h1), idet);
+                        const float fy = __fmul_rn(kahan_det(g22, h1, g12, h2), idet);
                         if (FUSE) L[j] = um_load(x, y, fx, fy, R0, R1, W, H);
                         else fout[(size_t)y * W + x] = make_float2(fx, fy);
                     }

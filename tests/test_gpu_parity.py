@@ -349,16 +349,27 @@ def _cv2_or_none():
         return None
 
 
-def _smooth_pair(W, H, seed, shift=(2, 3)):
+def _smooth_pair(W, H, seed, shift=(2.3, -1.7)):
+    """cv2-free pair with smooth, NON-INTEGER, spatially varying motion (a small affine map, bilinear sampling).
+    Integer translations put border pixels exactly on the in/out-of-bounds switch of A.8, where a 1e-7 change of
+    the flow flips the branch and moves a 15x15 neighbourhood by ~1e-2 px on cv2 itself."""
     rng = np.random.default_rng(seed)
-    a = rng.random((H // 4 + 8, W // 4 + 8)).astype(np.float32)
-    a = np.kron(a, np.ones((4, 4), np.float32))
+    pad = 24
+    a = rng.random(((H + 2 * pad) // 4 + 2, (W + 2 * pad) // 4 + 2)).astype(np.float32)
+    a = np.kron(a, np.ones((4, 4), np.float32))[:H + 2 * pad, :W + 2 * pad]
     for _ in range(4):
         a = (a + np.roll(a, 1, 0) + np.roll(a, -1, 0) + np.roll(a, 1, 1) + np.roll(a, -1, 1)) / 5
     a = (a - a.min()) / (a.max() - a.min()) * 255
-    f0 = a[8:8 + H, 8:8 + W].astype(np.uint8)
-    f1 = a[8 - shift[0]:8 - shift[0] + H, 8 + shift[1]:8 + shift[1] + W].astype(np.uint8)
-    return np.ascontiguousarray(f0), np.ascontiguousarray(f1)
+    f0 = a[pad:pad + H, pad:pad + W]
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+    sx = xs + pad + np.float32(shift[0]) + np.float32(0.0021) * ys - np.float32(0.0013) * xs
+    sy = ys + pad + np.float32(shift[1]) + np.float32(0.0017) * xs + np.float32(0.0011) * ys
+    x0 = np.floor(sx).astype(np.int64); y0 = np.floor(sy).astype(np.int64)
+    fx = sx - x0; fy = sy - y0
+    x0 = np.clip(x0, 0, a.shape[1] - 2); y0 = np.clip(y0, 0, a.shape[0] - 2)
+    f1 = (a[y0, x0] * (1 - fx) * (1 - fy) + a[y0, x0 + 1] * fx * (1 - fy) +
+          a[y0 + 1, x0] * (1 - fx) * fy + a[y0 + 1, x0 + 1] * fx * fy)
+    return np.ascontiguousarray(f0.astype(np.uint8)), np.ascontiguousarray(f1.astype(np.uint8))
 
 
 def test_1080p_reference_parameters(eng, oracle):
@@ -392,7 +403,7 @@ def test_1080p_reference_parameters(eng, oracle):
 def test_4k_gaussian_config(eng, oracle):
     """BASELINE configs[2]: 3840x2160, levels 5, poly_n 7, poly_sigma 1.5, OPTFLOW_FARNEBACK_GAUSSIAN."""
     kw = dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)
-    f0, f1 = _smooth_pair(3840, 2160, 22, shift=(3, 5))
+    f0, f1 = _smooth_pair(3840, 2160, 22, shift=(3.4, 5.2))
     flow = eng.calc(f0, f1, None, **kw)
     assert np.isfinite(flow).all()
     cv2 = _cv2_or_none()
