@@ -96,6 +96,7 @@ struct PyrArgs {
     float* T; size_t t_item;                        // floats
     float* I; size_t i_item;
     int pitch;                                      // row pitch of T and I (floats)
+    float tapsv[80];                                // the same taps by value (unrolled kernels read them from the constant bank)
 };
 
 static inline int divup(int a, int b) { return (a + b - 1) / b; }

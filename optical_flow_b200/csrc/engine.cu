@@ -41,6 +41,7 @@ struct Level {
     int k = 0, W = 0, H = 0, pitch = 0, ksize = 0;
     double sigma = 0, scale = 1;
     float* taps = nullptr;              // device, ksize floats
+    std::vector<float> taps_h;          // host copy
     int* sx = nullptr; float* ax = nullptr;     // bilinear tables (k >= 1)
     int* sy = nullptr; float* ay = nullptr;
     int* ux = nullptr; float* uax = nullptr;    // bilinear tables from scale k+1 to this scale (flow up-sample)
@@ -289,6 +290,7 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
         std::vector<float> taps;
         gaussian_taps(l.ksize, l.sigma, taps);
         if (int rc = dupload(ctx, pl, &l.taps, taps)) return rc;
+        l.taps_h = taps;
         std::vector<int> ix, iy; std::vector<float> wx, wy;
         linear_table(l.W, W, ix, wx);
         linear_table(l.H, H, iy, wy);
@@ -378,6 +380,7 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
             py.W = pl.W; py.H = pl.H; py.Wk = l.W; py.Hk = l.H; py.ksize = l.ksize; py.taps = l.taps;
             py.sx = l.sx; py.ax = l.ax; py.sy = l.sy; py.ay = l.ay;
             py.T = pl.T; py.t_item = pl.t_item; py.I = pl.I; py.i_item = pl.i_item; py.pitch = l.pitch;
+            for (size_t q = 0; q < l.taps_h.size() && q < 80; q++) py.tapsv[q] = l.taps_h[q];
             launch_pyr2(L, pl.dtype, py, count);
             PolyArgs a = pl.pa;
             a.src = pl.I; a.src_item = pl.i_item * sizeof(float); a.src_pitch = (size_t)l.pitch * sizeof(float);
@@ -977,6 +980,7 @@ int ofb_stage_level_image(ofb_context* ctx, const void* frame, int dtype, int W,
         py.W = W; py.H = H; py.Wk = Wk; py.Hk = Hk; py.ksize = ksize; py.taps = dtab + o_taps;
         py.sx = (const int*)(dtab + o_sx); py.ax = dtab + o_ax; py.sy = (const int*)(dtab + o_sy); py.ay = dtab + o_ay;
         py.T = dT; py.t_item = 0; py.I = dI; py.i_item = 0; py.pitch = pitch;
+        for (size_t q = 0; q < taps.size() && q < 80; q++) py.tapsv[q] = taps[q];
         launch_pyr2(L, dtype, py, 1);
     }
     CU(cudaGetLastError());

@@ -145,42 +145,36 @@ k_iter(IterArgs a)
 #pragma unroll
             for (int r = 0; r < R; r++) blkB[r] = src[(size_t)min(ys + M + 1 + r, H - 1) * pitch];
         }
-        if (a.prefetch) {
-            // Software prefetch into L2, one step (~R rows) ahead: the M rows the next V phase will load and
-            // the R0 / R1 rows the next S phase will read (R1 at the un-displaced position; flow displacements
-            // are small next to a step).  Turns DRAM-latency stalls of the gathers into L2 hits.
-            const int yn = ys + R;                       // first output row of the next step
-            if (yn < yend) {
-                constexpr int LPR_M = (IT_CW * 4 + 127) / 128 + 1;         // 128-byte lines per M row segment
-                constexpr int NM = 5 * R * LPR_M;
-                constexpr int LPR_A = (TW * 16 + 127) / 128 + 1, LPR_B = (TW * 4 + 127) / 128 + 1;
-                constexpr int NR = R * (LPR_A + LPR_B);
-                const int total = NM + (FUSE ? 2 * NR : 0);
-                for (int i = tid; i < total; i += IT_THREADS) {
-                    const char* p;
-                    if (i < NM) {
-                        int c = i / (R * LPR_M), rem = i - c * (R * LPR_M), r = rem / LPR_M, l = rem - r * LPR_M;
-                        int row = min(yn + M + 1 + r, H - 1);
-                        int col = max(x0 - M, 0) + 32 * l;
-                        if (col >= pitch) continue;
-                        p = (const char*)(a.Min + (size_t)z * a.m_item + (size_t)c * a.plane + (size_t)row * pitch + col);
-                    } else {
-                        int j = i - NM;
-                        const RView& Rv = (j < NR) ? R0 : R1;
-                        if (j >= NR) j -= NR;
-                        int r = j / (LPR_A + LPR_B), l = j - r * (LPR_A + LPR_B);
-                        int row = min(yn + r, H - 1);
-                        if (l < LPR_A) {
-                            int col = x0 + 8 * l;
-                            if (col >= pitch) continue;
-                            p = (const char*)(Rv.a + (size_t)row * Rv.pitch + col);
-                        } else {
-                            int col = x0 + 32 * (l - LPR_A);
-                            if (col >= pitch) continue;
-                            p = (const char*)(Rv.b + (size_t)row * Rv.pitch + col);
-                        }
-                    }
+        if (a.prefetch && ys + R < yend) {
+            // Software prefetch into L2, one step (R rows) ahead: the M rows the next V phase will load and the
+            // R0 / R1 rows the next S phase will read (R1 at the un-displaced position; flow displacements are
+            // small next to a step).  One or two prefetch instructions per thread.
+            const int yn = ys + R;                                   // first output row of the next step
+            if (tid < 5 * R * 4) {                                   // M: 5 channels x R rows x 4 lines (96 floats + slack)
+                const int c = tid / (R * 4), rem = tid - c * (R * 4), r = rem >> 2, l = rem & 3;
+                const int row = min(yn + M + 1 + r, H - 1);
+                const int col = max(x0 - M, 0) + 32 * l;
+                if (col < pitch) {
+                    const float* p = a.Min + (size_t)z * a.m_item + (size_t)c * a.plane + (size_t)row * pitch + col;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
+            }
+            if (FUSE) {
+                constexpr int LA = (TW * 16 + 127) / 128 + 1;        // 128-byte lines per row of the float4 part
+                if (tid < R * LA) {
+                    const int r = tid / LA, l = tid - r * LA;
+                    const int row = min(yn + r, H - 1), col = x0 + 8 * l;
+                    if (col < pitch) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R0.a + (size_t)row * pitch + col));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R1.a + (size_t)row * pitch + col));
+                    }
+                } else if (tid < R * LA + R * 4) {
+                    const int j = tid - R * LA, r = j >> 2, l = j & 3;
+                    const int row = min(yn + r, H - 1), col = x0 + 32 * l;
+                    if (col < pitch) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R0.b + (size_t)row * pitch + col));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R1.b + (size_t)row * pitch + col));
+                    }
                 }
             }
         }
@@ -349,12 +343,12 @@ static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
         attr_set = true;
     }
     const int xt = divup(a.W, TW);
-    // aim at >= 2 CTAs per SM for ONE pair; strips are whole steps of R rows.  The partition must not depend
+    // aim at ~1 CTA per SM for ONE pair; strips are whole steps of R rows.  The partition must not depend
     // on the batch size: the van Herk blocks restart at strip boundaries, so it fixes the f32 rounding, and a
     // pair must give bit-identical results whether it is processed alone or inside a batch.
-    int want = std::max(1, (2 * sm_count + xt - 1) / xt);
+    int want = std::max(1, (sm_count + xt - 1) / xt);       // ~one CTA per SM for a single pair; batches bring the rest
     int strip = divup(divup(a.H, want), R) * R;
-    strip = std::max(strip, std::min(a.H, 2 * R));          // keep the block-A preload amortised
+    strip = std::max(strip, std::min(a.H, 4 * R));          // the block-A preload of a strip costs one step: keep it <= 25 %
     strip = divup(strip, R) * R;
     a.strip_rows = strip;
     a.prefetch = g_iter_prefetch;

@@ -179,8 +179,109 @@ k_pyr_v2(PyrArgs a)
     a.I[(size_t)z * a.i_item + (size_t)y * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
 }
 
+// Unrolled row / column passes for the kernel sizes of pyr_scale = 0.5 (3, 9, 19, 39, 79 and 5): taps come from the
+// constant bank, no loop or tap-load overhead.  Same arithmetic and order as k_pyr_h2 / k_pyr_v2 (bit-identical).
+template <typename T, int KS>
+__global__ void __launch_bounds__(256)
+k_pyr_h4(PyrArgs a)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, r = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (x >= a.Wk || r >= a.H) return;
+    constexpr int c = KS / 2;
+    const int W = a.W;
+    const int sx = a.sx[x];
+    const float a1 = a.ax[x], a0 = 1.f - a1;
+    const T* row = (const T*)((const char*)a.src + (size_t)z * a.src_item + (size_t)r * a.src_pitch);
+    float b0 = 0.f, b1 = 0.f;
+    if (sx - c >= 0 && sx + 1 + c < W) {
+        const T* p = row + sx - c;
+        if (a1 != 0.f) {
+            float prev = px_to_f32(p[0]);
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                float cur = px_to_f32(p[j + 1]);
+                b0 += a.tapsv[j] * prev;
+                b1 += a.tapsv[j] * cur;
+                prev = cur;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KS; j++) b0 += a.tapsv[j] * px_to_f32(p[j]);
+        }
+    } else {
+        int sx1 = min(sx + 1, W - 1);
+#pragma unroll 1
+        for (int j = 0; j < KS; j++) {
+            float t = a.taps[j];
+            b0 += t * px_to_f32(row[reflect101(sx + j - c, W)]);
+            if (a1 != 0.f) b1 += t * px_to_f32(row[reflect101(sx1 + j - c, W)]);
+        }
+    }
+    a.T[(size_t)z * a.t_item + (size_t)r * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256)
+k_pyr_v4(PyrArgs a)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (x >= a.Wk || y >= a.Hk) return;
+    constexpr int c = KS / 2;
+    const int H = a.H;
+    const int sy = a.sy[y];
+    const float a1 = a.ay[y], a0 = 1.f - a1;
+    const int sy1 = min(sy + 1, H - 1);
+    const float* T = a.T + (size_t)z * a.t_item + x;
+    float b0 = 0.f, b1 = 0.f;
+    if (sy - c >= 0 && sy + 1 + c < H) {
+        const float* p = T + (size_t)(sy - c) * a.pitch;
+        if (a1 != 0.f) {
+            float prev = p[0];
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                float cur = p[(size_t)(j + 1) * a.pitch];
+                b0 += a.tapsv[j] * prev;
+                b1 += a.tapsv[j] * cur;
+                prev = cur;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KS; j++) b0 += a.tapsv[j] * p[(size_t)j * a.pitch];
+        }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < KS; j++) {
+            float t = a.taps[j];
+            b0 += t * T[(size_t)reflect101(sy + j - c, H) * a.pitch];
+            if (a1 != 0.f) b1 += t * T[(size_t)reflect101(sy1 + j - c, H) * a.pitch];
+        }
+    }
+    a.I[(size_t)z * a.i_item + (size_t)y * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
+}
+
+template <int KS>
+static void run_pyr4(Launch& L, int dtype, const PyrArgs& a, int batch)
+{
+    dim3 block(64, 4);
+    dim3 gh(divup(a.Wk, 64), divup(a.H, 4), batch), gv(divup(a.Wk, 64), divup(a.Hk, 4), batch);
+    L.run(dtype == 0 ? "pyr_h_u8" : "pyr_h_f32", [&](cudaStream_t s) {
+        if (dtype == 0) k_pyr_h4<uint8_t, KS><<<gh, block, 0, s>>>(a);
+        else k_pyr_h4<float, KS><<<gh, block, 0, s>>>(a);
+    });
+    L.run("pyr_v", [&](cudaStream_t s) { k_pyr_v4<KS><<<gv, block, 0, s>>>(a); });
+}
+
 void launch_pyr2(Launch& L, int dtype, const PyrArgs& a, int batch)
 {
+    switch (a.ksize) {
+        case 3: run_pyr4<3>(L, dtype, a, batch); return;
+        case 5: run_pyr4<5>(L, dtype, a, batch); return;
+        case 9: run_pyr4<9>(L, dtype, a, batch); return;
+        case 19: run_pyr4<19>(L, dtype, a, batch); return;
+        case 39: run_pyr4<39>(L, dtype, a, batch); return;
+        case 79: run_pyr4<79>(L, dtype, a, batch); return;
+        default: break;
+    }
     dim3 block(64, 4);
     dim3 gh(divup(a.Wk, 64), divup(a.H, 4), batch), gv(divup(a.Wk, 64), divup(a.Hk, 4), batch);
     L.run(dtype == 0 ? "pyr_h_u8" : "pyr_h_f32", [&](cudaStream_t s) {
