@@ -36,7 +36,9 @@ template <int SRC>   // 0 zero flow, 1 read flow, 2 up-sample coarse flow
 __global__ void __launch_bounds__(256)
 k_um0(Um0Args a)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, z = blockIdx.z;
+    // blockIdx.x = batch item (fastest-varying in dispatch order): the CTAs of consecutive pairs for the same tile
+    // run together, so the frame slot pair z reads as R1 and pair z+1 reads as R0 comes from HBM once.
+    const int x = blockIdx.y * 32 + threadIdx.x, y = blockIdx.z * 8 + threadIdx.y, z = blockIdx.x;
     if (x >= a.W || y >= a.H) return;
     float dx = 0.f, dy = 0.f;
     if (SRC == 1) {
@@ -64,7 +66,7 @@ k_um0(Um0Args a)
 
 void launch_um0(Launch& L, int src, const Um0Args& a, int batch)
 {
-    dim3 block(32, 8), grid(divup(a.W, 32), divup(a.H, 8), batch);
+    dim3 block(32, 8), grid(batch, divup(a.W, 32), divup(a.H, 8));
     const char* names[3] = {"um0_zero", "um0_flow", "um0_upsample"};
     L.run(names[src], [&](cudaStream_t s) {
         if (src == 0) k_um0<0><<<grid, block, 0, s>>>(a);
@@ -105,10 +107,10 @@ k_iter(IterArgs a)
     float* sV = it_smem;                      // 5 * R * IT_VP
     float* sH = it_smem + 5 * R * IT_VP;      // 5 * R * HP
 
-    const int tid = threadIdx.x, z = blockIdx.z;
+    const int tid = threadIdx.x, z = blockIdx.x;            // batch item fastest-varying (see k_um0)
     const int W = a.W, H = a.H;
-    const int x0 = blockIdx.x * TW;
-    const int ybeg = blockIdx.y * a.strip_rows;
+    const int x0 = blockIdx.y * TW;
+    const int ybeg = blockIdx.z * a.strip_rows;
     const int yend = min(ybeg + a.strip_rows, H);
     if (ybeg >= H) return;
 
@@ -352,7 +354,7 @@ static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
     strip = divup(strip, R) * R;
     a.strip_rows = strip;
     a.prefetch = g_iter_prefetch;
-    dim3 grid(xt, divup(a.H, strip), batch);
+    dim3 grid(batch, xt, divup(a.H, strip));
     L.run(GAUSS ? (FUSE ? "iter_fused_gauss" : "iter_last_gauss") : (FUSE ? "iter_fused" : "iter_last"), [&](cudaStream_t s) {
         k_iter<M, FUSE, ILP, GAUSS><<<grid, IT_THREADS, smem, s>>>(a);
     });

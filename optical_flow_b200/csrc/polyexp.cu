@@ -182,7 +182,7 @@ void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const Po
 // register window for 4 outputs.
 // ------------------------------------------------------------------------------------------------
 template <int N, int SRC>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_polyexp2(PolyArgs a)
 {
     constexpr int TW = 64, TH = 16;
