@@ -69,6 +69,7 @@ struct IterArgs {
     float2* flow; size_t flow_item;
     int W, H, strip_rows; float c;          // c = 1e-3 * winsize^4
     int prefetch;                           // 1 = software-prefetch the next step's lines into L2
+    int reverse;                            // 1 = walk the grid backwards: the tiles the previous launch wrote last (still in L2) are read first
     unsigned* minmax;                       // non-null (FUSE = false only): fold min / max of |flow| of item z into minmax[2z..]
     int gauss;                              // 1 = Gaussian window (flags & 256): taps gk[0..M], c = 1e-3
     float gk[17];

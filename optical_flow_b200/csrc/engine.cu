@@ -92,6 +92,7 @@ struct ofb_context {
     bool generic = false;
     int batch = 0;                      // pairs per launch inside a shot (0 = choose from the frame size)
     int batch0 = 0;                     // pairs per launch at scale 0 (0 = same as batch)
+    bool alt_order = false;             // alternate the grid direction of consecutive iteration launches (L2 reuse of M)
     Plan plan;
     unsigned* minmax = nullptr;         // 2 per batch item
     double* sumacc = nullptr;           // 1 per batch item
@@ -450,6 +451,7 @@ bool solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                     a.gauss = gaussian ? 1 : 0;
                     if (gaussian) for (size_t q = 0; q < pl.gk.size() && q < 17; q++) a.gk[q] = pl.gk[q];
                     a.minmax = (fold_minmax && last && k == 0) ? ctx->minmax + 2 * z0 : nullptr;
+                    a.reverse = (ctx->alt_order && (i % 2 == 0)) ? 1 : 0;     // um0 wrote M forwards; alternate from there
                     launch_iter(L, a, p.winsize, !last, nb, ctx->sm_count);
                     cur ^= 1;
                 }
@@ -1126,6 +1128,7 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
 {
     if (!ctx || !name) return OFB_ERR_BAD_ARG;
     if (!strcmp(name, "generic_kernels")) { ctx->generic = value != 0; return OFB_OK; }
+    if (!strcmp(name, "alt_order")) { ctx->alt_order = value != 0; return OFB_OK; }
     if (!strcmp(name, "iter_ilp")) { set_iter_ilp(value); return OFB_OK; }
     if (!strcmp(name, "iter_prefetch")) { set_iter_prefetch(value); return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }

@@ -107,10 +107,14 @@ k_iter(IterArgs a)
     float* sV = it_smem;                      // 5 * R * IT_VP
     float* sH = it_smem + 5 * R * IT_VP;      // 5 * R * HP
 
-    const int tid = threadIdx.x, z = blockIdx.x;            // batch item fastest-varying (see k_um0)
+    // batch item fastest-varying (see k_um0); optionally the whole grid order reversed (IterArgs::reverse)
+    const int tid = threadIdx.x;
+    const int z = a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int bx = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int bs = a.reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
     const int W = a.W, H = a.H;
-    const int x0 = blockIdx.y * TW;
-    const int ybeg = blockIdx.z * a.strip_rows;
+    const int x0 = bx * TW;
+    const int ybeg = bs * a.strip_rows;
     const int yend = min(ybeg + a.strip_rows, H);
     if (ybeg >= H) return;
 

@@ -266,6 +266,76 @@ def test_degenerate_parameters_are_finite(eng, oracle):
     assert mx <= 1e-3 * max(1.0, float(np.abs(ref).max())), (mean, mx)
 
 
+@pytest.mark.parametrize("W,H", [(8, 8), (16, 9), (5, 40), (1, 50), (50, 1), (2, 2), (31, 33), (100, 7), (97, 131)])
+def test_tiny_and_odd_frames(eng, oracle, W, H):
+    """cv2 accepts any frame size (scales that would be < 32 px are dropped); so must the kernels."""
+    rng = np.random.default_rng(W * 100 + H)
+    a = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    b = np.roll(a, 1, 1)
+    kw = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    for generic in (0, 1):
+        eng.set_option("generic_kernels", generic)
+        try:
+            f = eng.calc(a, b, None, **kw)
+        finally:
+            eng.set_option("generic_kernels", 0)
+        ref = oracle.farneback(a, b, None, **kw)
+        assert f.shape == (H, W, 2) and np.isfinite(f).all()
+        mean, mx = epe(f, ref)
+        assert mx <= 1e-3 * max(1.0, float(np.abs(ref).max())), (W, H, generic, mean, mx)
+    pic = eng.pair(a, b, want_bgr=True, want_magsum=True, want_flow=True, **kw)
+    assert np.array_equal(pic["bgr"], oracle.viz(pic["flow"], 0))
+
+
+@pytest.mark.parametrize("kw", [dict(winsize=41), dict(winsize=64, iterations=2), dict(poly_n=9, poly_sigma=2.0), dict(poly_n=2),
+                                dict(winsize=41, flags=256), dict(pyr_scale=0.8, levels=6), dict(pyr_scale=0.3, levels=2),
+                                dict(winsize=33, poly_n=7, iterations=1)])
+def test_parameters_outside_the_fast_paths(eng, oracle, kw):
+    """winsize > 33, poly_n not in {3,5,7}, unusual pyr_scale: generic kernels, same results."""
+    f0, f1 = _smooth_pair(352, 288, 41)
+    p = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    p.update(kw)
+    flow = eng.calc(f0, f1, None, **p)
+    ref = oracle.farneback(f0, f1, None, **p)
+    mean, mx = epe(flow, ref)
+    print("params %s: mean %.2e max %.2e" % (kw, mean, mx))
+    assert mean <= EPE_MEAN_TOL and mx <= EPE_MAX_TOL, (kw, mean, mx)
+
+
+def test_device_pointer_entry_points_and_pitch(eng):
+    """ofb_farneback_device / ofb_flow_to_bgr_device / ofb_sum_magnitude_device with a row pitch larger than the row."""
+    import ctypes as C
+    from optical_flow_b200 import _lib, make_params
+    L = _lib.load()
+    f0, f1 = _smooth_pair(200, 120, 43)
+    H, W = f0.shape
+    pitch = 256
+    pad0 = np.zeros((H, pitch), np.uint8); pad0[:, :W] = f0
+    pad1 = np.zeros((H, pitch), np.uint8); pad1[:, :W] = f1
+    d0, d1 = eng.device_alloc(pad0.nbytes), eng.device_alloc(pad1.nbytes)
+    dflow, dbgr, dsum = eng.device_alloc(W * H * 8), eng.device_alloc(W * H * 3), eng.device_alloc(4)
+    eng.h2d(d0, pad0); eng.h2d(d1, pad1)
+    prm = make_params()
+    vp = C.c_void_p
+    assert L.ofb_farneback_device(eng._h, vp(d0), vp(d1), 0, W, H, pitch, pitch, vp(dflow), C.byref(prm)) == 0
+    assert L.ofb_flow_to_bgr_device(eng._h, vp(dflow), W, H, vp(dbgr)) == 0
+    assert L.ofb_sum_magnitude_device(eng._h, vp(dflow), W, H, vp(dsum)) == 0
+    flow = np.empty((H, W, 2), np.float32); bgr = np.empty((H, W, 3), np.uint8); sm = np.empty(1, np.float32)
+    eng.d2h(flow, dflow); eng.d2h(bgr, dbgr); eng.d2h(sm, dsum)
+    ref = eng.calc(f0, f1, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    assert np.array_equal(flow, ref)
+    assert np.array_equal(bgr, eng.flow_to_bgr(ref))
+    assert abs(float(sm[0]) - float(eng.sum_magnitude(ref))) <= 1e-6 * float(sm[0])
+    for p in (d0, d1, dflow, dbgr, dsum):
+        eng.device_free(p)
+    # error paths of the C ABI: status codes, messages, no exceptions
+    bad = make_params(pyr_scale=1.0)
+    assert L.ofb_farneback_device(eng._h, vp(1), vp(1), 0, W, H, 0, 0, vp(1), C.byref(bad)) == _lib.OFB_ERR_ASSERT
+    assert b"pyrScale_ < 1" in L.ofb_last_error(eng._h)
+    assert L.ofb_farneback_device(eng._h, vp(None), vp(1), 0, W, H, 0, 0, vp(1), C.byref(prm)) == _lib.OFB_ERR_BAD_ARG
+    assert L.ofb_set_option(eng._h, b"no_such_option", 1) == _lib.OFB_ERR_BAD_ARG
+
+
 # ------------------------------------------------------------------------------------------------
 # fused pair / shot forms
 # ------------------------------------------------------------------------------------------------
