@@ -317,8 +317,17 @@ def run_ours(args, rank, local_rank, world):
             kernels[name] = k
         dom = max((kv for kv in kernels.items() if "achieved_gbs" in kv[1]), key=lambda kv: kv[1]["total_ms"], default=None)
         if dom:
+            # measured DRAM bytes of the same kernel from the committed `ncu --set full` capture, per launch like `achieved`
+            traffic, traffic_src = None, None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))
+                per_pair = tj["kernels"][dom[0]]["dram_bytes_per_pair"]
+                traffic = round(per_pair * P / dom[1]["launches"], 1) if (W, H) == (1920, 1080) else None
+                traffic_src = "profiles/r1d_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": round(dom[1]["achieved_gbs"] / peak, 4), "traffic": None,
+                    "frac": round(dom[1]["achieved_gbs"] / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                     "alg_bytes_per_launch": dom[1]["alg_bytes_per_launch"],
                     "avg_launch_ms": round(dom[1]["total_ms"] / dom[1]["launches"], 5),
                     "share_of_step": dom[1]["share"], "peak_source": peak_src,
