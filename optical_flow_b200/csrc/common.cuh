@@ -171,7 +171,6 @@ void set_iter_prefetch(int v);
 void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count);
 
 // blur_solve.cu -- A.9 / A.10
-void set_sm_count(int n);
 void launch_blur_solve_box(Launch& L, Planes5 M, int W, int H, int winsize, double* tmp /* 5 planes f64 */,
                            float2* flow, bool generic);
 void launch_blur_solve_gauss(Launch& L, Planes5 M, int W, int H, int winsize, const float* half_taps,

@@ -567,7 +567,6 @@ int ofb_create(int device, ofb_context** out)
     ctx = c;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    set_sm_count(c->sm_count);
     cudaError_t rc = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (rc == cudaSuccess) rc = r; };
     ok(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
