@@ -221,6 +221,7 @@ def run_ours(args, rank, local_rank, world):
 
     W, H, P = args.width, args.height, args.pairs
     n = W * H
+    numa_cpus = dist.bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     eng = ofb.Farneback(local_rank)          # raises if the CUDA library / device is missing: no fallback
     if args.batch > 0:
         eng.set_option("batch", args.batch)
@@ -354,7 +355,8 @@ def run_ours(args, rank, local_rank, world):
                            "l2": "inputs larger than L2: every step streams %d MB of frames and %d MB of pictures "
                                  "plus ~300 MB of per-pair intermediates through a 126 MB L2"
                                  % (frames.nbytes // 2**20, bgr_host.nbytes // 2**20),
-                           "sharding": "one %d-pair shot per GPU, no collective" % P},
+                           "sharding": "one %d-pair shot per GPU, no collective" % P,
+                           "host_affinity": ("rank bound to %d CPUs near its GPU (NVML)" % numa_cpus) if numa_cpus else "default"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
                         "d2h_bytes_per_step": int(bgr_host.nbytes), "ms_per_step": t_e2e / args.steps},
                 "gpu_launches": int(launches),

@@ -23,8 +23,39 @@ def init(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs closest to its GPU (NVML's ideal CPU affinity) BEFORE pinned host buffers are
+    allocated, so that they are first-touched on the GPU's NUMA node.  With several ranks per box the frames and
+    pictures of each rank then cross one PCIe root complex and one memory controller, not the socket interconnect.
+    Returns the number of CPUs bound to, or 0 when NVML / affinity control is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
 
 
 def _device():

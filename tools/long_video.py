@@ -34,6 +34,7 @@ def main():
     rank, local_rank, world = dist.env_rank()
     if world > 1:
         dist.init("nccl")
+        dist.bind_to_gpu_numa_node(local_rank)
     W, H = args.width, args.height
     rng = np.random.default_rng(args.seed)
     lengths = []
