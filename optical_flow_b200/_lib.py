@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libofb200.so")
+# OFB_LIB_PATH selects another build of the SAME library (A/B runs of a kernel change on one GPU box).
+LIB_PATH = os.environ.get("OFB_LIB_PATH") or os.path.join(_HERE, "lib", "libofb200.so")
 
 OFB_OK = 0
 OFB_ERR_CUDA = -1

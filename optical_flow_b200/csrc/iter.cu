@@ -218,7 +218,9 @@ k_iter(IterArgs a)
 
         // ---- H phase: item = (channel*R + row, segment) ----
         if (tid < 5 * R * NSEG) {
-            const int seg = tid % NSEG, rc = tid / NSEG;
+            // lanes of a warp = consecutive (channel,row) lines of ONE segment: both pitches are odd, so the
+            // lanes' reads of sV and writes of sH fall in distinct banks
+            const int seg = tid / (5 * R), rc = tid - seg * (5 * R);
             const int xa = seg * R;
             const float* v = sV + rc * IT_VP + xa;
             float* h = sH + rc * HP + xa;
