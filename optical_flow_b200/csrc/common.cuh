@@ -95,6 +95,7 @@ struct PyrArgs {
     const int* sx; const float* ax;                 // per destination column: source index, weight of the next one
     const int* sy; const float* ay;                 // per destination row
     float* T; size_t t_item;                        // floats
+    size_t t_cap;                                   // floats available per item of T (the column-first path stores Hk x W there)
     float* I; size_t i_item;
     int pitch;                                      // row pitch of T and I (floats)
     float tapsv[80];                                // the same taps by value (unrolled kernels read them from the constant bank)

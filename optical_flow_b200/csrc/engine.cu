@@ -380,7 +380,7 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
             py.src = d_frames; py.src_item = item_bytes; py.src_pitch = pitch_bytes;
             py.W = pl.W; py.H = pl.H; py.Wk = l.W; py.Hk = l.H; py.ksize = l.ksize; py.taps = l.taps;
             py.sx = l.sx; py.ax = l.ax; py.sy = l.sy; py.ay = l.ay;
-            py.T = pl.T; py.t_item = pl.t_item; py.I = pl.I; py.i_item = pl.i_item; py.pitch = l.pitch;
+            py.T = pl.T; py.t_item = pl.t_item; py.t_cap = pl.t_item; py.I = pl.I; py.i_item = pl.i_item; py.pitch = l.pitch;
             for (size_t q = 0; q < l.taps_h.size() && q < 80; q++) py.tapsv[q] = l.taps_h[q];
             launch_pyr2(L, pl.dtype, py, count);
             PolyArgs a = pl.pa;
@@ -953,7 +953,8 @@ int ofb_stage_level_image(ofb_context* ctx, const void* frame, int dtype, int W,
     size_t esz = dtype == OFB_U8 ? 1 : 4;
     float *dfr, *dT, *dI, *dtab;
     if (int rc = stage_buf(ctx, 0, (size_t)W * H * esz, &dfr)) return rc;
-    if (int rc = stage_buf(ctx, 1, sizeof(float) * (size_t)H * pitch, &dT)) return rc;
+    const size_t t_cap = std::max((size_t)H * pitch, (size_t)Hk * W);
+    if (int rc = stage_buf(ctx, 1, sizeof(float) * t_cap, &dT)) return rc;
     if (int rc = stage_buf(ctx, 2, sizeof(float) * (size_t)Hk * pitch, &dI)) return rc;
     std::vector<float> taps;
     gaussian_taps(ksize, sigma, taps);
@@ -980,7 +981,7 @@ int ofb_stage_level_image(ofb_context* ctx, const void* frame, int dtype, int W,
         py.src = dfr; py.src_item = 0; py.src_pitch = (size_t)W * esz;
         py.W = W; py.H = H; py.Wk = Wk; py.Hk = Hk; py.ksize = ksize; py.taps = dtab + o_taps;
         py.sx = (const int*)(dtab + o_sx); py.ax = dtab + o_ax; py.sy = (const int*)(dtab + o_sy); py.ay = dtab + o_ay;
-        py.T = dT; py.t_item = 0; py.I = dI; py.i_item = 0; py.pitch = pitch;
+        py.T = dT; py.t_item = 0; py.t_cap = t_cap; py.I = dI; py.i_item = 0; py.pitch = pitch;
         for (size_t q = 0; q < taps.size() && q < 80; q++) py.tapsv[q] = taps[q];
         launch_pyr2(L, dtype, py, 1);
     }

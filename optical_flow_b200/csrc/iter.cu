@@ -103,6 +103,7 @@ k_iter(IterArgs a)
     constexpr int TW = IT_CW - 2 * M;
     constexpr int HP = TW + 1;
     constexpr int NSEG = (TW + R - 1) / R;
+    static_assert(TW >= 1 && 5 * R * NSEG <= IT_THREADS, "H phase: one thread per (channel, row, segment)");
     extern __shared__ float it_smem[];
     float* sV = it_smem;                      // 5 * R * IT_VP
     float* sH = it_smem + 5 * R * IT_VP;      // 5 * R * HP

@@ -259,10 +259,152 @@ k_pyr_v4(PyrArgs a)
     a.I[(size_t)z * a.i_item + (size_t)y * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Column-first variant of the unrolled passes (the fast path when rows are 4-pixel aligned).  The row-first
+// kernels above spend ~140 instructions per frame pixel, almost all of it single-byte loads: every output column
+// re-reads KS+1 neighbouring bytes.  Running the COLUMN pass first turns those into aligned 4-pixel loads shared by
+// four outputs, and it shrinks the image to Hk rows before the (strided) row pass runs:
+//   k_pyr_vf : T'(y, x) = (1-ay) * Vblur(sy, x) + ay * Vblur(sy+1, x)      for all W source columns, Hk rows
+//   k_pyr_hf : I(y, x)  = (1-ax) * Hblur_T'(y, sx) + ax * Hblur_T'(y, sx+1)
+// The four operators are linear and separable, so this is the same level image up to f32 rounding order
+// (tests/test_gpu_parity.py::test_stage_level_image, 2e-4 on a 0..255 scale).
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Px4;
+template <> struct Px4<unsigned char> {
+    static __device__ __forceinline__ void load(const unsigned char* p, float v[4])
+    {
+        const unsigned w = *reinterpret_cast<const unsigned*>(p);
+        // byte i of w into the mantissa of 2^23 (one PRMT), minus 2^23: u8 -> f32 without the XU pipe
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | i)) - 8388608.f;
+    }
+};
+template <> struct Px4<float> {
+    static __device__ __forceinline__ void load(const float* p, float v[4])
+    {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+};
+
+template <typename T, int KS>
+__global__ void __launch_bounds__(256)
+k_pyr_vf(PyrArgs a)
+{
+    const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (x4 >= a.W || y >= a.Hk) return;
+    constexpr int c = KS / 2;
+    const int H = a.H;
+    const int sy = a.sy[y];
+    const float a1 = a.ay[y], a0 = 1.f - a1;
+    const char* base = (const char*)a.src + (size_t)z * a.src_item + (size_t)x4 * sizeof(T);
+    float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sy - c >= 0 && sy + 1 + c < H) {
+        const char* p = base + (size_t)(sy - c) * a.src_pitch;
+        if (a1 != 0.f) {
+            float prev[4], cur[4];
+            Px4<T>::load((const T*)p, prev);
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                Px4<T>::load((const T*)(p + (size_t)(j + 1) * a.src_pitch), cur);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    b0[i] += a.tapsv[j] * prev[i];
+                    b1[i] += a.tapsv[j] * cur[i];
+                    prev[i] = cur[i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                float v[4];
+                Px4<T>::load((const T*)(p + (size_t)j * a.src_pitch), v);
+#pragma unroll
+                for (int i = 0; i < 4; i++) b0[i] += a.tapsv[j] * v[i];
+            }
+        }
+    } else {
+        const int sy1 = min(sy + 1, H - 1);
+#pragma unroll 1
+        for (int j = 0; j < KS; j++) {
+            const float t = a.taps[j];
+            float v[4];
+            Px4<T>::load((const T*)(base + (size_t)reflect101(sy + j - c, H) * a.src_pitch), v);
+#pragma unroll
+            for (int i = 0; i < 4; i++) b0[i] += t * v[i];
+            if (a1 != 0.f) {
+                Px4<T>::load((const T*)(base + (size_t)reflect101(sy1 + j - c, H) * a.src_pitch), v);
+#pragma unroll
+                for (int i = 0; i < 4; i++) b1[i] += t * v[i];
+            }
+        }
+    }
+    float4 o;
+    if (a1 != 0.f) o = make_float4(b0[0] * a0 + b1[0] * a1, b0[1] * a0 + b1[1] * a1, b0[2] * a0 + b1[2] * a1, b0[3] * a0 + b1[3] * a1);
+    else o = make_float4(b0[0], b0[1], b0[2], b0[3]);
+    *reinterpret_cast<float4*>(a.T + (size_t)z * a.t_item + (size_t)y * a.W + x4) = o;       // T': Hk rows of W floats
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256)
+k_pyr_hf(PyrArgs a)
+{
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z;
+    if (x >= a.Wk || y >= a.Hk) return;
+    constexpr int c = KS / 2;
+    const int W = a.W;
+    const int sx = a.sx[x];
+    const float a1 = a.ax[x], a0 = 1.f - a1;
+    const float* row = a.T + (size_t)z * a.t_item + (size_t)y * W;
+    float b0 = 0.f, b1 = 0.f;
+    if (sx - c >= 0 && sx + 1 + c < W) {
+        const float* p = row + sx - c;
+        if (a1 != 0.f) {
+            float prev = p[0];
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                float cur = p[j + 1];
+                b0 += a.tapsv[j] * prev;
+                b1 += a.tapsv[j] * cur;
+                prev = cur;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KS; j++) b0 += a.tapsv[j] * p[j];
+        }
+    } else {
+        const int sx1 = min(sx + 1, W - 1);
+#pragma unroll 1
+        for (int j = 0; j < KS; j++) {
+            const float t = a.taps[j];
+            b0 += t * row[reflect101(sx + j - c, W)];
+            if (a1 != 0.f) b1 += t * row[reflect101(sx1 + j - c, W)];
+        }
+    }
+    a.I[(size_t)z * a.i_item + (size_t)y * a.pitch + x] = (a1 != 0.f) ? b0 * a0 + b1 * a1 : b0;
+}
+
+static bool pyr_colfirst_ok(int dtype, const PyrArgs& a)
+{
+    const size_t al = dtype == 0 ? 4 : 16;            // bytes of one 4-pixel load
+    return a.W % 4 == 0 && a.src_pitch % al == 0 && a.src_item % al == 0 && ((uintptr_t)a.src % al) == 0 &&
+           (size_t)a.Hk * a.W <= a.t_cap && a.t_item % 4 == 0 && ((uintptr_t)a.T % 16) == 0;
+}
+
 template <int KS>
 static void run_pyr4(Launch& L, int dtype, const PyrArgs& a, int batch)
 {
     dim3 block(64, 4);
+    if (pyr_colfirst_ok(dtype, a)) {
+        dim3 gv(divup(a.W / 4, 64), divup(a.Hk, 4), batch), gh(divup(a.Wk, 64), divup(a.Hk, 4), batch);
+        L.run(dtype == 0 ? "pyr_v_u8" : "pyr_v_f32", [&](cudaStream_t s) {
+            if (dtype == 0) k_pyr_vf<uint8_t, KS><<<gv, block, 0, s>>>(a);
+            else k_pyr_vf<float, KS><<<gv, block, 0, s>>>(a);
+        });
+        L.run("pyr_h", [&](cudaStream_t s) { k_pyr_hf<KS><<<gh, block, 0, s>>>(a); });
+        return;
+    }
     dim3 gh(divup(a.Wk, 64), divup(a.H, 4), batch), gv(divup(a.Wk, 64), divup(a.Hk, 4), batch);
     L.run(dtype == 0 ? "pyr_h_u8" : "pyr_h_f32", [&](cudaStream_t s) {
         if (dtype == 0) k_pyr_h4<uint8_t, KS><<<gh, block, 0, s>>>(a);
