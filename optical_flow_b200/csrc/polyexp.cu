@@ -201,13 +201,48 @@ k_polyexp2(PolyArgs a)
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const unsigned char* srcb = (const unsigned char*)a.src + (size_t)z * a.src_item;
 
-    if (SRC == 0) {
-        for (int i = tid; i < PH * PW; i += 256) {
-            int py = i / PW, px = i - py * PW;
-            int gy = min(max(y0 + py - N, 0), H - 1), gx = min(max(x0 + px - N, 0), W - 1);
-            sI[i] = ((const float*)(srcb + (size_t)gy * a.src_pitch))[gx];
+    // Vertical pass, column-thread form: thread = (patch column px, row group g); group g owns output rows
+    // 5g .. 5g+5 (rows 5 and 10 are produced twice with identical values).  The thread pulls its 6+2N input values
+    // straight into registers -- from global memory (SRC 0) or from the row-blurred patch (SRC 1, interior tiles), in
+    // which case the column pass of the pre-blur is applied on the fly -- so the level image never sits in shared
+    // memory and two block-wide passes (and their barriers) disappear.  Same arithmetic, same order as the tiled form.
+    constexpr int VG = 3, VR = 6, VS = 5;               // groups, rows per group, row stride between groups
+    static_assert(VS * (VG - 1) + VR == TH && VG * PW <= 256, "vertical pass: thread = (column, row group)");
+    auto vertical_from = [&](const float (&b)[VR + 2 * N], int g, int px) {
+#pragma unroll
+        for (int o = 0; o < VR; o++) {
+            const int cidx = o + N;
+            float r0 = b[cidx] * a.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                float lo = b[cidx - k], hi = b[cidx + k];
+                float p = lo + hi;
+                r0 = r0 + a.g[k] * p;
+                r1 = r1 + a.xg[k] * (hi - lo);
+                r2 = r2 + a.xxg[k] * p;
+            }
+            const int ty = VS * g + o;
+            sR0[ty * RP + px] = (double)r0;
+            sR1[ty * RP + px] = (double)r1;
+            sR2[ty * RP + px] = (double)r2;
         }
-        __syncthreads();
+    };
+    bool vertical_done = false;                          // block-uniform
+
+    if (SRC == 0) {
+        if (tid < VG * PW) {
+            const int g = tid / PW, px = tid - g * PW;
+            const int gx = min(max(x0 + px - N, 0), W - 1);
+            const float* colp = (const float*)srcb + gx;
+            float b[VR + 2 * N];
+#pragma unroll
+            for (int i = 0; i < VR + 2 * N; i++) {
+                const int gy = min(max(y0 - N + VS * g + i, 0), H - 1);
+                b[i] = *(const float*)((const char*)colp + (size_t)gy * a.src_pitch);
+            }
+            vertical_from(b, g, px);
+        }
+        vertical_done = true;
     } else {
         // raw patch: raw[j][i] = frame(reflect101(y0-N-1+j), reflect101(x0-N-1+i))
         float* raw = sI;
@@ -217,18 +252,42 @@ k_polyexp2(PolyArgs a)
         const bool interior = (SRC == 1) && x0 >= 8 && x0 + TW + 8 <= W && uby >= 0 && uby + RAWH <= H &&
                               ((a.src_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(srcb) & 3) == 0);
         if (interior) {
+            // row pass of the pre-blur while loading: 4 outputs per aligned 4-pixel load (+ the two neighbour bytes)
             constexpr int NVEC = (TW + 16) / 4;
-            constexpr int SHIFT = 7 - N;               // raw column c = (column offset inside the superset) - SHIFT
+            constexpr int HBP = TW + 16;                 // sHB column = column offset inside the superset
+            float* sHBf = sI;
             for (int i = tid; i < RAWH * NVEC; i += 256) {
-                int j = i / NVEC, v = i - j * NVEC;
-                const uchar4 q = *reinterpret_cast<const uchar4*>(srcb + (size_t)(uby + j) * a.src_pitch + (x0 - 8) + 4 * v);
-                float* dst = raw + j * RAWW + 4 * v - SHIFT;
-                const int c0 = 4 * v - SHIFT;
-                if (c0 >= 0 && c0 < RAWW) dst[0] = u8_to_f32(q.x);
-                if (c0 + 1 >= 0 && c0 + 1 < RAWW) dst[1] = u8_to_f32(q.y);
-                if (c0 + 2 >= 0 && c0 + 2 < RAWW) dst[2] = u8_to_f32(q.z);
-                if (c0 + 3 >= 0 && c0 + 3 < RAWW) dst[3] = u8_to_f32(q.w);
+                const int j = i / NVEC, v = i - j * NVEC;
+                const unsigned char* p = srcb + (size_t)(uby + j) * a.src_pitch + (x0 - 8) + 4 * v;
+                const uchar4 q = *reinterpret_cast<const uchar4*>(p);
+                const unsigned char lb = v > 0 ? p[-1] : q.x, rb = v < NVEC - 1 ? p[4] : q.w;   // ends: outputs unused
+                const float fl = u8_to_f32(lb), f0 = u8_to_f32(q.x), f1 = u8_to_f32(q.y), f2 = u8_to_f32(q.z),
+                            f3 = u8_to_f32(q.w), fr = u8_to_f32(rb);
+                float4 o;
+                o.x = 0.25f * fl; o.x = o.x + 0.5f * f0; o.x = o.x + 0.25f * f1;
+                o.y = 0.25f * f0; o.y = o.y + 0.5f * f1; o.y = o.y + 0.25f * f2;
+                o.z = 0.25f * f1; o.z = o.z + 0.5f * f2; o.z = o.z + 0.25f * f3;
+                o.w = 0.25f * f2; o.w = o.w + 0.5f * f3; o.w = o.w + 0.25f * fr;
+                *reinterpret_cast<float4*>(sHBf + j * HBP + 4 * v) = o;
             }
+            __syncthreads();
+            if (tid < VG * PW) {
+                const int g = tid / PW, px = tid - g * PW;
+                const float* h = sHBf + (VS * g) * HBP + px + (8 - N);     // raw row of patch row 5g is 5g (+0,+1,+2)
+                float b[VR + 2 * N];
+                float h0 = h[0], h1 = h[HBP];
+#pragma unroll
+                for (int i = 0; i < VR + 2 * N; i++) {
+                    const float h2 = h[(i + 2) * HBP];
+                    float acc = 0.25f * h0;
+                    acc = acc + 0.5f * h1;
+                    acc = acc + 0.25f * h2;
+                    b[i] = acc;
+                    h0 = h1; h1 = h2;
+                }
+                vertical_from(b, g, px);
+            }
+            vertical_done = true;
         } else {
             for (int i = tid; i < RAWH * RAWW; i += 256) {
                 int j = i / RAWW, ii = i - j * RAWW;
@@ -236,48 +295,50 @@ k_polyexp2(PolyArgs a)
                 const unsigned char* row = srcb + (size_t)fy * a.src_pitch;
                 raw[i] = (SRC == 1) ? u8_to_f32(row[fx]) : ((const float*)row)[fx];
             }
+            __syncthreads();
+            // row pass at the (replicate-clamped) patch columns
+            for (int i = tid; i < RAWH * PW; i += 256) {
+                int j = i / PW, px = i - j * PW;
+                int cx = min(max(x0 - N + px, 0), W - 1) - ubx;            // raw column of the centre tap
+                const float* r = raw + j * RAWW + cx;
+                float acc = 0.25f * r[-1];
+                acc = acc + 0.5f * r[0];
+                acc = acc + 0.25f * r[1];
+                sHB[i] = acc;
+            }
+            __syncthreads();
+            // column pass at the (replicate-clamped) patch rows; overwrites the raw patch
+            for (int i = tid; i < PH * PW; i += 256) {
+                int py = i / PW, px = i - py * PW;
+                int cy = min(max(y0 - N + py, 0), H - 1) - uby;
+                const float* c = sHB + cy * PW + px;
+                float acc = 0.25f * c[-PW];
+                acc = acc + 0.5f * c[0];
+                acc = acc + 0.25f * c[PW];
+                sI[i] = acc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // row pass at the (replicate-clamped) patch columns
-        for (int i = tid; i < RAWH * PW; i += 256) {
-            int j = i / PW, px = i - j * PW;
-            int cx = min(max(x0 - N + px, 0), W - 1) - ubx;            // raw column of the centre tap
-            const float* r = raw + j * RAWW + cx;
-            float acc = 0.25f * r[-1];
-            acc = acc + 0.5f * r[0];
-            acc = acc + 0.25f * r[1];
-            sHB[i] = acc;
-        }
-        __syncthreads();
-        // column pass at the (replicate-clamped) patch rows; overwrites the raw patch
-        for (int i = tid; i < PH * PW; i += 256) {
-            int py = i / PW, px = i - py * PW;
-            int cy = min(max(y0 - N + py, 0), H - 1) - uby;
-            const float* c = sHB + cy * PW + px;
-            float acc = 0.25f * c[-PW];
-            acc = acc + 0.5f * c[0];
-            acc = acc + 0.25f * c[PW];
-            sI[i] = acc;
-        }
-        __syncthreads();
     }
 
-    // ---- vertical pass (f32, cv2's order), results widened once ----
-    for (int i = tid; i < TH * PW; i += 256) {
-        int ty = i / PW, px = i - ty * PW;
-        const float* col = sI + (ty + N) * PW + px;
-        float r0 = col[0] * a.g[0], r1 = 0.f, r2 = 0.f;
+    // ---- vertical pass, tiled form (border tiles of the fused scale-0 path): f32 in cv2's order, widened once ----
+    if (!vertical_done) {
+        for (int i = tid; i < TH * PW; i += 256) {
+            int ty = i / PW, px = i - ty * PW;
+            const float* col = sI + (ty + N) * PW + px;
+            float r0 = col[0] * a.g[0], r1 = 0.f, r2 = 0.f;
 #pragma unroll
-        for (int k = 1; k <= N; k++) {
-            float lo = col[-k * PW], hi = col[k * PW];
-            float p = lo + hi;
-            r0 = r0 + a.g[k] * p;
-            r1 = r1 + a.xg[k] * (hi - lo);
-            r2 = r2 + a.xxg[k] * p;
+            for (int k = 1; k <= N; k++) {
+                float lo = col[-k * PW], hi = col[k * PW];
+                float p = lo + hi;
+                r0 = r0 + a.g[k] * p;
+                r1 = r1 + a.xg[k] * (hi - lo);
+                r2 = r2 + a.xxg[k] * p;
+            }
+            sR0[ty * RP + px] = (double)r0;
+            sR1[ty * RP + px] = (double)r1;
+            sR2[ty * RP + px] = (double)r2;
         }
-        sR0[ty * RP + px] = (double)r0;
-        sR1[ty * RP + px] = (double)r1;
-        sR2[ty * RP + px] = (double)r2;
     }
     __syncthreads();
 
@@ -354,7 +415,7 @@ static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
 {
     constexpr int TW = 64, TH = 16, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1);
     size_t smem = sizeof(double) * 3 * TH * RP +
-                  sizeof(float) * (SRC == 0 ? (size_t)PH * PW : (size_t)(PH + 2) * (PW + 2) + (size_t)(PH + 2) * PW);
+                  sizeof(float) * (SRC == 0 ? (size_t)0 : (size_t)(PH + 2) * (PW + 2) + (size_t)(PH + 2) * PW);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_polyexp2<N, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
