@@ -247,43 +247,86 @@ k_polyexp2(PolyArgs a)
         // raw patch: raw[j][i] = frame(reflect101(y0-N-1+j), reflect101(x0-N-1+i))
         float* raw = sI;
         const int ubx = x0 - N - 1, uby = y0 - N - 1;
-        // interior tiles of a u8 frame: no border arithmetic, 4 pixels per load from the 4-byte aligned
-        // superset [x0-8, x0+TW+8) of the needed columns
-        const bool interior = (SRC == 1) && x0 >= 8 && x0 + TW + 8 <= W && uby >= 0 && uby + RAWH <= H &&
-                              ((a.src_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(srcb) & 3) == 0);
-        if (interior) {
+        // u8 frames with 4-byte aligned rows: 4 pixels per load from the aligned superset [x0-8, x0+TW+8) of the
+        // needed columns.  Interior tiles need no border arithmetic at all; border tiles take the same two passes with
+        // reflect-101 (pre-blur taps) / replicate (patch) indices computed per element.
+        const bool aligned = (SRC == 1) && (W & 3) == 0 && W >= 8 && ((a.src_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(srcb) & 3) == 0);
+        const bool xin = x0 >= 8 && x0 + TW + 8 <= W, yin = uby >= 0 && uby + RAWH <= H;
+        if (aligned) {
             // row pass of the pre-blur while loading: 4 outputs per aligned 4-pixel load (+ the two neighbour bytes)
             constexpr int NVEC = (TW + 16) / 4;
             constexpr int HBP = TW + 16;                 // sHB column = column offset inside the superset
+            constexpr int NIT = (RAWH * NVEC + 255) / 256;
             float* sHBf = sI;
-            for (int i = tid; i < RAWH * NVEC; i += 256) {
-                const int j = i / NVEC, v = i - j * NVEC;
-                const unsigned char* p = srcb + (size_t)(uby + j) * a.src_pitch + (x0 - 8) + 4 * v;
-                const uchar4 q = *reinterpret_cast<const uchar4*>(p);
-                const unsigned char lb = v > 0 ? p[-1] : q.x, rb = v < NVEC - 1 ? p[4] : q.w;   // ends: outputs unused
-                const float fl = u8_to_f32(lb), f0 = u8_to_f32(q.x), f1 = u8_to_f32(q.y), f2 = u8_to_f32(q.z),
-                            f3 = u8_to_f32(q.w), fr = u8_to_f32(rb);
-                float4 o;
-                o.x = 0.25f * fl; o.x = o.x + 0.5f * f0; o.x = o.x + 0.25f * f1;
-                o.y = 0.25f * f0; o.y = o.y + 0.5f * f1; o.y = o.y + 0.25f * f2;
-                o.z = 0.25f * f1; o.z = o.z + 0.5f * f2; o.z = o.z + 0.25f * f3;
-                o.w = 0.25f * f2; o.w = o.w + 0.5f * f3; o.w = o.w + 0.25f * fr;
-                *reinterpret_cast<float4*>(sHBf + j * HBP + 4 * v) = o;
+            if (xin) {
+                uchar4 q[NIT]; unsigned char lb[NIT], rb[NIT];
+#pragma unroll
+                for (int k = 0; k < NIT; k++) {          // all loads of the thread in flight before the first use
+                    const int i = tid + 256 * k;
+                    if (i < RAWH * NVEC) {
+                        const int j = i / NVEC, v = i - j * NVEC;
+                        const int fy = yin ? uby + j : reflect101(uby + j, H);
+                        const unsigned char* p = srcb + (size_t)fy * a.src_pitch + (x0 - 8) + 4 * v;
+                        q[k] = *reinterpret_cast<const uchar4*>(p);
+                        lb[k] = v > 0 ? p[-1] : q[k].x;             // ends of the superset: those outputs are unused
+                        rb[k] = v < NVEC - 1 ? p[4] : q[k].w;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NIT; k++) {
+                    const int i = tid + 256 * k;
+                    if (i < RAWH * NVEC) {
+                        const int j = i / NVEC, v = i - j * NVEC;
+                        const float fl = u8_to_f32(lb[k]), f0 = u8_to_f32(q[k].x), f1 = u8_to_f32(q[k].y), f2 = u8_to_f32(q[k].z),
+                                    f3 = u8_to_f32(q[k].w), fr = u8_to_f32(rb[k]);
+                        float4 o;
+                        o.x = 0.25f * fl; o.x = o.x + 0.5f * f0; o.x = o.x + 0.25f * f1;
+                        o.y = 0.25f * f0; o.y = o.y + 0.5f * f1; o.y = o.y + 0.25f * f2;
+                        o.z = 0.25f * f1; o.z = o.z + 0.5f * f2; o.z = o.z + 0.25f * f3;
+                        o.w = 0.25f * f2; o.w = o.w + 0.5f * f3; o.w = o.w + 0.25f * fr;
+                        *reinterpret_cast<float4*>(sHBf + j * HBP + 4 * v) = o;
+                    }
+                }
+            } else {
+                for (int i = tid; i < RAWH * HBP; i += 256) {
+                    const int j = i / HBP, cc = i - j * HBP;
+                    const int c = x0 - 8 + cc;
+                    if (c >= 0 && c < W) {
+                        const unsigned char* row = srcb + (size_t)reflect101(uby + j, H) * a.src_pitch;
+                        float acc = 0.25f * u8_to_f32(row[reflect101(c - 1, W)]);
+                        acc = acc + 0.5f * u8_to_f32(row[c]);
+                        acc = acc + 0.25f * u8_to_f32(row[reflect101(c + 1, W)]);
+                        sHBf[i] = acc;
+                    }
+                }
             }
             __syncthreads();
             if (tid < VG * PW) {
                 const int g = tid / PW, px = tid - g * PW;
-                const float* h = sHBf + (VS * g) * HBP + px + (8 - N);     // raw row of patch row 5g is 5g (+0,+1,+2)
+                const float* hcol = sHBf + (min(max(x0 - N + px, 0), W - 1) - (x0 - 8));      // replicate-clamped patch column
                 float b[VR + 2 * N];
-                float h0 = h[0], h1 = h[HBP];
+                if (yin) {
+                    const float* h = hcol + (VS * g) * HBP;          // patch row r <- row-blurred rows r, r+1, r+2
+                    float h0 = h[0], h1 = h[HBP];
 #pragma unroll
-                for (int i = 0; i < VR + 2 * N; i++) {
-                    const float h2 = h[(i + 2) * HBP];
-                    float acc = 0.25f * h0;
-                    acc = acc + 0.5f * h1;
-                    acc = acc + 0.25f * h2;
-                    b[i] = acc;
-                    h0 = h1; h1 = h2;
+                    for (int i = 0; i < VR + 2 * N; i++) {
+                        const float h2 = h[(i + 2) * HBP];
+                        float acc = 0.25f * h0;
+                        acc = acc + 0.5f * h1;
+                        acc = acc + 0.25f * h2;
+                        b[i] = acc;
+                        h0 = h1; h1 = h2;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VR + 2 * N; i++) {
+                        const int cy = min(max(y0 - N + VS * g + i, 0), H - 1) - uby;      // replicate-clamped patch row
+                        const float* h = hcol + cy * HBP;
+                        float acc = 0.25f * h[-HBP];
+                        acc = acc + 0.5f * h[0];
+                        acc = acc + 0.25f * h[HBP];
+                        b[i] = acc;
+                    }
                 }
                 vertical_from(b, g, px);
             }
