@@ -17,6 +17,10 @@
  *                         the loop body                                visualize_optical_flow.py:37-55 (picture)
  *   ofb_shot_*            the sequential per-pair loops                visualize_optical_flow.py:21-63,
  *                                                                      optical_flow.py:83-99
+ *   ofb_bgr_to_gray_*     cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)      optical_flow.py:44,
+ *                                                                      visualize_optical_flow.py:31,35
+ *   ofb_resize_u8_*       cv2.resize(frame, (w, h))  [INTER_LINEAR]    optical_flow.py:25-31
+ *   ofb_*_bgr_host        the same loops fed with the DECODED BGR frames (resize / gray conversion on the GPU)
  *
  * Plain C: pointers and sizes only, no C++ or torch types.  All functions return 0 on success or
  * a negative ofb_status; none throws.  ofb_last_error() gives the message for the last failure on
@@ -36,7 +40,7 @@
 extern "C" {
 #endif
 
-#define OFB_ABI_VERSION 1
+#define OFB_ABI_VERSION 2
 
 /* flags of cv2.calcOpticalFlowFarneback */
 #define OFB_OPTFLOW_USE_INITIAL_FLOW 4
@@ -121,6 +125,23 @@ int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, i
                    const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms);
 int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int W, int H, const ofb_params* p,
                     uint8_t* d_bgr, float* d_magsum, float* d_flow, float* device_ms);
+
+/* ---- frame preprocessing on the GPU -------------------
+ * Both are integer algorithms and bit-exact against cv2 (tests/golden/preprocess.npz).
+ * ofb_bgr_to_gray_host: (H, W, 3) uint8 BGR -> (H, W) uint8, gray = (3735 B + 19235 G + 9798 R + 16384) >> 15.
+ * ofb_resize_u8_host:   cv2.resize(src, (dW, dH)) with the default INTER_LINEAR for 1 or 3 interleaved channels;
+ *                       to_gray != 0 (3 channels only) applies the gray conversion to the resized pixel and writes
+ *                       (dH, dW) uint8 -- read_frame of optical_flow.py:34-46 in one pass.
+ * ofb_shot_bgr_host / ofb_pairs_bgr_host: as ofb_shot_host / ofb_pairs_host, but the frames are the decoded BGR
+ * frames (n, H, W, 3); dW = dH = 0 keeps the size, otherwise every frame is first resized to dW x dH.  All outputs
+ * have the size of the gray frames (dW x dH).  `gray` (may be NULL) receives the n gray frames. */
+int ofb_bgr_to_gray_host(ofb_context* ctx, const uint8_t* bgr, int W, int H, uint8_t* gray);
+int ofb_resize_u8_host(ofb_context* ctx, const uint8_t* src, int W, int H, int channels, int dW, int dH, int to_gray,
+                       uint8_t* dst);
+int ofb_shot_bgr_host(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames, int W, int H, int dW, int dH,
+                      const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, uint8_t* gray, float* device_ms);
+int ofb_pairs_bgr_host(ofb_context* ctx, const uint8_t* prev_bgr, const uint8_t* next_bgr, int n_pairs, int W, int H,
+                       int dW, int dH, const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms);
 
 /* ---- per-stage entry points (parity tests; host arrays in cv2's layouts) ---
  * R and M are (H, W, 5) float32 interleaved as in OpenCV; flow is (H, W, 2). */

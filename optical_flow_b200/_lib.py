@@ -80,6 +80,10 @@ def load():
     proto("ofb_shot_host", i, vp, vp, i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_shot_device", i, vp, vp, i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_pairs_host", i, vp, vp, vp, i, i, i, pp, vp, vp, vp, fp)
+    proto("ofb_bgr_to_gray_host", i, vp, vp, i, i, vp)
+    proto("ofb_resize_u8_host", i, vp, vp, i, i, i, i, i, i, vp)
+    proto("ofb_shot_bgr_host", i, vp, vp, i, i, i, i, i, pp, vp, vp, vp, vp, fp)
+    proto("ofb_pairs_bgr_host", i, vp, vp, vp, i, i, i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_scale_count", i, i, i, C.c_double, i)
     proto("ofb_scale_geometry", i, i, i, C.c_double, i, ip, ip, ip, dp)
     proto("ofb_stage_level_image", i, vp, vp, i, i, i, C.c_double, i, vp)

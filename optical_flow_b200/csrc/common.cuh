@@ -177,6 +177,16 @@ void launch_blur_solve_box(Launch& L, Planes5 M, int W, int H, int winsize, doub
 void launch_blur_solve_gauss(Launch& L, Planes5 M, int W, int H, int winsize, const float* half_taps,
                              float* tmp /* 5 planes f32 */, float2* flow, bool generic);
 
+// preprocess.cu -- SURVEY.md 8f row N2: BGR->gray and the 8-bit bilinear resize, batched over frames
+struct ResizeTab {             // per destination column / row: the two source indices and their 11-bit weights
+    const int* x0; const int* x1; const short* ax;     // ax[2x], ax[2x+1]
+    const int* y0; const int* y1; const short* ay;
+};
+void launch_bgr2gray(Launch& L, const uint8_t* src, size_t src_item, size_t src_pitch, uint8_t* dst, size_t dst_item,
+                     size_t dst_pitch, int W, int H, int batch);
+void launch_resize_u8(Launch& L, const uint8_t* src, size_t src_item, size_t src_pitch, int cn, bool to_gray, uint8_t* dst,
+                      size_t dst_item, size_t dst_pitch, int dW, int dH, const ResizeTab& t, int batch);
+
 // viz.cu -- Appendix B
 // batched over pairs: flow / bgr / minmax / sums advance by *_item per batch element
 void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax /* 2 per item */,

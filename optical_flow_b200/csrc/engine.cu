@@ -99,6 +99,10 @@ struct ofb_context {
     float* sumout = nullptr;            // device staging of magnitude sums (batch items)
     float* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
+    // 8-bit bilinear resize tables of the last (source, destination) geometry (preprocess.cu)
+    int rs_geom[4] = {0, 0, 0, 0};      // sW, sH, dW, dH
+    int* rs_tab = nullptr;              // x0[dW] x1[dW] y0[dH] y1[dH] | short ax[2dW] ay[2dH]
+    ResizeTab rs{};
 };
 
 namespace {
@@ -527,6 +531,66 @@ int no_initial_flow(ofb_context* ctx, const ofb_params* p)
     return 0;
 }
 
+
+// ---- frame preprocessing ---------------------------------------------------------------------
+// Source indices and 11-bit weights of cv::resize(INTER_LINEAR) for 8-bit images, as cv2 builds them: the coordinate
+// (d + 0.5) * scale - 0.5 is formed in double and rounded to f32 before the floor; columns move an out-of-range index
+// inside and zero its fraction, rows only clip the two indices (oracle/preprocess_oracle.c coord_u8).
+void resize_coord(int d, double scale, int slen, bool clamp_weights, int* s0, int* s1, short* w)
+{
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(f);
+    f -= (float)s;
+    if (clamp_weights) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= slen - 1) { s = slen - 1; f = 0.f; }
+    }
+    *s0 = std::min(std::max(s, 0), slen - 1);
+    *s1 = std::min(std::max(s + 1, 0), slen - 1);
+    w[0] = (short)std::lrint((1.f - f) * 2048.f);
+    w[1] = (short)std::lrint(f * 2048.f);
+}
+
+int ensure_resize(ofb_context* ctx, int sW, int sH, int dW, int dH)
+{
+    if (ctx->rs_tab && ctx->rs_geom[0] == sW && ctx->rs_geom[1] == sH && ctx->rs_geom[2] == dW && ctx->rs_geom[3] == dH) return 0;
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    if (ctx->rs_tab) { cudaFree(ctx->rs_tab); ctx->rs_tab = nullptr; }
+    const size_t nint = 2 * (size_t)dW + 2 * (size_t)dH;
+    std::vector<int> buf(nint + (nint + 1) / 2);            // ints, then the shorts (2 per destination coordinate)
+    int *x0 = buf.data(), *x1 = x0 + dW, *y0 = x1 + dW, *y1 = y0 + dH;
+    short* ax = reinterpret_cast<short*>(buf.data() + nint);
+    short* ay = ax + 2 * (size_t)dW;
+    const double sx = 1.0 / ((double)dW / sW), sy = 1.0 / ((double)dH / sH);
+    for (int x = 0; x < dW; x++) resize_coord(x, sx, sW, true, &x0[x], &x1[x], ax + 2 * x);
+    for (int y = 0; y < dH; y++) resize_coord(y, sy, sH, false, &y0[y], &y1[y], ay + 2 * y);
+    CU(cudaMalloc((void**)&ctx->rs_tab, buf.size() * sizeof(int)));
+    CU(cudaMemcpy(ctx->rs_tab, buf.data(), buf.size() * sizeof(int), cudaMemcpyHostToDevice));
+    int* d = ctx->rs_tab;
+    const short* dax = reinterpret_cast<const short*>(d + nint);
+    ctx->rs = ResizeTab{d, d + dW, dax, d + 2 * dW, d + 2 * dW + dH, dax + 2 * (size_t)dW};
+    ctx->rs_geom[0] = sW; ctx->rs_geom[1] = sH; ctx->rs_geom[2] = dW; ctx->rs_geom[3] = dH;
+    return 0;
+}
+
+// `count` decoded BGR frames (sW x sH, tightly packed, src_item bytes apart) -> gray frames of dW x dH (gray_item apart):
+// cv2.resize (only when the size changes) followed by cvtColor(BGR2GRAY), optical_flow.py:42-44.
+void preprocess_frames(ofb_context* ctx, Launch& L, const uint8_t* d_src, size_t src_item, int sW, int sH, uint8_t* d_gray,
+                       size_t gray_item, int dW, int dH, int count)
+{
+    if (sW == dW && sH == dH) launch_bgr2gray(L, d_src, src_item, (size_t)sW * 3, d_gray, gray_item, (size_t)dW, dW, dH, count);
+    else launch_resize_u8(L, d_src, src_item, (size_t)sW * 3, 3, true, d_gray, gray_item, (size_t)dW, dW, dH, ctx->rs, count);
+}
+
+// Geometry check of the BGR entry points; dW / dH = 0 means "no resize".
+int bgr_geometry(ofb_context* ctx, int sW, int sH, int* dW, int* dH)
+{
+    if (sW <= 0 || sH <= 0 || *dW < 0 || *dH < 0 || ((*dW == 0) != (*dH == 0))) return fail(ctx, OFB_ERR_BAD_ARG, "bad frame or target size");
+    if (*dW == 0) { *dW = sW; *dH = sH; }
+    if (*dW != sW || *dH != sH) return ensure_resize(ctx, sW, sH, *dW, *dH);
+    return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -600,6 +664,7 @@ void ofb_destroy(ofb_context* ctx)
     ctx->prof.collect();
     free_plan(ctx->plan);
     for (int i = 0; i < 6; i++) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    if (ctx->rs_tab) cudaFree(ctx->rs_tab);
     cudaFree(ctx->minmax); cudaFree(ctx->sumacc); cudaFree(ctx->sumout);
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_frame_free[i]);
@@ -874,8 +939,10 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
     return OFB_OK;
 }
 
-int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p,
-                  uint8_t* bgr, float* magsum, float* flow, float* device_ms)
+// Shared body of ofb_shot_host (sW = 0: frames are gray, W x H) and ofb_shot_bgr_host (frames are decoded BGR frames of
+// sW x sH; the gray frames of W x H are produced on the GPU, optionally returned through gray_out).
+static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, int sW, int sH, const ofb_params* p,
+                          uint8_t* bgr, float* magsum, float* flow, uint8_t* gray_out, float* device_ms)
 {
     if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
     if (!frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
@@ -886,8 +953,17 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
     Plan& pl = ctx->plan;
     cudaStream_t sc = ctx->s_compute, su = ctx->s_h2d, sd = ctx->s_d2h;
     const size_t n = (size_t)W * H;
+    const bool from_bgr = sW > 0;
+    const size_t sn = from_bgr ? (size_t)sW * sH * 3 : n;                // bytes of one source frame
     float* d_sums = nullptr;
     if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)(n_frames - 1), &d_sums)) return rc;
+    uint8_t *bs0 = nullptr, *bs[2] = {nullptr, nullptr};                   // BGR staging: first frame, two chunks
+    if (from_bgr) {
+        float* q;
+        const size_t sna = (sn + 15) & ~(size_t)15;
+        if (int rc = stage_buf(ctx, 4, sna * (2 * (size_t)B + 1), &q)) return rc;
+        bs0 = (uint8_t*)q; bs[0] = bs0 + sna; bs[1] = bs[0] + sna * B;
+    }
     Launch L{sc, &ctx->prof};
     const int n_pairs = n_frames - 1;
     const int n_chunks = (n_pairs + B - 1) / B;
@@ -896,11 +972,11 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
     // Uploads run ahead on s_h2d (frames of chunk c go to fstage[c & 1]), results drain on s_d2h
     // (pictures / flows of chunk c sit in bgr[c & 1] / flow0[c & 1]); the compute stream only waits on
     // the events it needs, so H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c.
-    CU(cudaMemcpyAsync(pl.f0, frames, n, cudaMemcpyHostToDevice, su));
+    CU(cudaMemcpyAsync(from_bgr ? bs0 : pl.f0, frames, sn, cudaMemcpyHostToDevice, su));
     auto upload = [&](int c) -> int {
         const int t0 = c * B, b = std::min(B, n_pairs - t0), par = c & 1;
         if (c >= 2) CU(cudaStreamWaitEvent(su, ctx->ev_frame_free[par], 0));
-        CU(cudaMemcpyAsync(pl.fstage[par], frames + (size_t)(t0 + 1) * n, (size_t)b * n, cudaMemcpyHostToDevice, su));
+        CU(cudaMemcpyAsync(from_bgr ? bs[par] : pl.fstage[par], frames + (size_t)(t0 + 1) * sn, (size_t)b * sn, cudaMemcpyHostToDevice, su));
         CU(cudaEventRecord(ctx->ev_h2d[par], su));
         return 0;
     };
@@ -909,6 +985,14 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
         const int t0 = c * B, b = std::min(B, n_pairs - t0), par = c & 1;
         if (c + 1 < n_chunks) if (int rc = upload(c + 1)) return rc;
         CU(cudaStreamWaitEvent(sc, ctx->ev_h2d[par], 0));
+        if (from_bgr) {
+            if (c == 0) preprocess_frames(ctx, L, bs0, sn, sW, sH, pl.f0, n, W, H, 1);
+            preprocess_frames(ctx, L, bs[par], sn, sW, sH, pl.fstage[par], n, W, H, b);
+            if (gray_out) {          // the gray frames the reference would have computed on the host (stream-ordered copy)
+                if (c == 0) CU(cudaMemcpyAsync(gray_out, pl.f0, n, cudaMemcpyDeviceToHost, sc));
+                CU(cudaMemcpyAsync(gray_out + (size_t)(t0 + 1) * n, pl.fstage[par], (size_t)b * n, cudaMemcpyDeviceToHost, sc));
+            }
+        }
         if (c == 0) expand_frames(ctx, L, pl.f0, n, (size_t)W, 0, 1);
         expand_frames(ctx, L, pl.fstage[par], n, (size_t)W, t0 + 1, b);
         CU(cudaEventRecord(ctx->ev_frame_free[par], sc));
@@ -929,6 +1013,104 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
     CU(cudaStreamSynchronize(sc));
     CU(cudaStreamSynchronize(su));
     if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
+    return OFB_OK;
+}
+
+int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p,
+                  uint8_t* bgr, float* magsum, float* flow, float* device_ms)
+{
+    return shot_host_impl(ctx, frames, n_frames, W, H, 0, 0, p, bgr, magsum, flow, nullptr, device_ms);
+}
+
+int ofb_shot_bgr_host(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames, int W, int H, int dW, int dH,
+                      const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, uint8_t* gray, float* device_ms)
+{
+    if (!ctx) return OFB_ERR_BAD_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = bgr_geometry(ctx, W, H, &dW, &dH)) return rc;
+    return shot_host_impl(ctx, bgr_frames, n_frames, dW, dH, W, H, p, bgr, magsum, flow, gray, device_ms);
+}
+
+int ofb_pairs_bgr_host(ofb_context* ctx, const uint8_t* prev_bgr, const uint8_t* next_bgr, int n_pairs, int W, int H, int dW, int dH,
+                       const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms)
+{
+    if (!ctx) return OFB_ERR_BAD_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = bgr_geometry(ctx, W, H, &dW, &dH)) return rc;
+    if (int rc = validate(ctx, dW, dH, OFB_U8, p)) return rc;
+    if (!prev_bgr || !next_bgr || n_pairs < 1) return fail(ctx, OFB_ERR_BAD_ARG, "need at least one pair");
+    if (int rc = no_initial_flow(ctx, p)) return rc;
+    const int B = shot_batch(ctx, dW, dH, n_pairs);
+    if (int rc = ensure_plan(ctx, dW, dH, OFB_U8, p, B)) return rc;
+    Plan& pl = ctx->plan;
+    cudaStream_t s = ctx->s_compute;
+    const size_t n = (size_t)dW * dH, sn = (size_t)W * H * 3;
+    float* d_sums = nullptr;
+    if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)n_pairs, &d_sums)) return rc;
+    float* q;
+    if (int rc = stage_buf(ctx, 4, sn * 2 * (size_t)B + 32, &q)) return rc;
+    uint8_t* bs[2] = {(uint8_t*)q, (uint8_t*)q + ((sn * B + 15) & ~(size_t)15)};
+    Launch L{s, &ctx->prof};
+    CU(cudaEventRecord(ctx->ev_t0, s));
+    for (int t0 = 0; t0 < n_pairs; t0 += B) {
+        const int b = std::min(B, n_pairs - t0);
+        CU(cudaMemcpyAsync(bs[0], prev_bgr + (size_t)t0 * sn, (size_t)b * sn, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(bs[1], next_bgr + (size_t)t0 * sn, (size_t)b * sn, cudaMemcpyHostToDevice, s));
+        preprocess_frames(ctx, L, bs[0], sn, W, H, pl.fstage[0], n, dW, dH, b);
+        preprocess_frames(ctx, L, bs[1], sn, W, H, pl.fstage[1], n, dW, dH, b);
+        expand_frames(ctx, L, pl.fstage[0], n, (size_t)dW, 0, b, 2);     // prev[z] -> slot 2z
+        expand_frames(ctx, L, pl.fstage[1], n, (size_t)dW, 1, b, 2);     // next[z] -> slot 2z+1
+        const bool mm = solve_pairs(ctx, L, 0, b, pl.flow0[0], n, 2, bgr != nullptr);
+        if (bgr) picture(ctx, L, pl.flow0[0], n, n, pl.bgr[0], n * 3, b, mm);
+        if (magsum) launch_sum_magnitude_batch(L, pl.flow0[0], n, n, ctx->sumacc, d_sums + t0, b);
+        CU(cudaGetLastError());
+        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[0], (size_t)b * n * 3, cudaMemcpyDeviceToHost, s));
+        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[0], (size_t)b * n * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (magsum) CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(ctx->ev_t1, s));
+    CU(cudaStreamSynchronize(s));
+    if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
+    return OFB_OK;
+}
+
+// ---- frame preprocessing on its own (parity tests) ---------------------------------------------
+int ofb_bgr_to_gray_host(ofb_context* ctx, const uint8_t* bgr, int W, int H, uint8_t* gray)
+{
+    if (!ctx || !bgr || !gray || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * H;
+    float *ds, *dd;
+    if (int rc = stage_buf(ctx, 0, n * 3 + 16, &ds)) return rc;
+    if (int rc = stage_buf(ctx, 1, n + 16, &dd)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    CU(cudaMemcpyAsync(ds, bgr, n * 3, cudaMemcpyHostToDevice, s));
+    Launch L{s, &ctx->prof};
+    launch_bgr2gray(L, (const uint8_t*)ds, 0, (size_t)W * 3, (uint8_t*)dd, 0, (size_t)W, W, H, 1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(gray, dd, n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
+}
+
+int ofb_resize_u8_host(ofb_context* ctx, const uint8_t* src, int W, int H, int channels, int dW, int dH, int to_gray, uint8_t* dst)
+{
+    if (!ctx || !src || !dst || W <= 0 || H <= 0 || dW <= 0 || dH <= 0 || (channels != 1 && channels != 3) || (to_gray && channels != 3))
+        return fail(ctx, OFB_ERR_BAD_ARG, "bad argument (channels must be 1 or 3; to_gray needs 3)");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_resize(ctx, W, H, dW, dH)) return rc;
+    const size_t sn = (size_t)W * H * channels, dn = (size_t)dW * dH * (to_gray ? 1 : channels);
+    float *ds, *dd;
+    if (int rc = stage_buf(ctx, 0, sn + 16, &ds)) return rc;
+    if (int rc = stage_buf(ctx, 1, dn + 16, &dd)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    CU(cudaMemcpyAsync(ds, src, sn, cudaMemcpyHostToDevice, s));
+    Launch L{s, &ctx->prof};
+    launch_resize_u8(L, (const uint8_t*)ds, 0, (size_t)W * channels, channels, to_gray != 0, (uint8_t*)dd, 0,
+                     (size_t)dW * (to_gray ? 1 : channels), dW, dH, ctx->rs, 1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst, dd, dn, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return OFB_OK;
 }
 

@@ -241,6 +241,72 @@ class Farneback:
                                            C.byref(dev_ms)))
         return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
 
+    # -- frame preprocessing on the GPU -------------------------------------------
+    def bgr_to_gray(self, bgr):
+        """cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) for (H, W, 3) uint8 (optical_flow.py:44, visualize_optical_flow.py:31,35)."""
+        bgr = np.ascontiguousarray(bgr)
+        if bgr.ndim != 3 or bgr.shape[2] != 3 or bgr.dtype != np.uint8:
+            raise ValueError("bgr must be (H, W, 3) uint8")
+        H, W = bgr.shape[:2]
+        gray = np.empty((H, W), np.uint8)
+        self._check(self._L.ofb_bgr_to_gray_host(self._h, _ptr(bgr), W, H, _ptr(gray)), "cvtColor")
+        return gray
+
+    def resize(self, src, dsize, to_gray=False):
+        """cv2.resize(src, (w, h)) with the default INTER_LINEAR, uint8, 1 or 3 channels (optical_flow.py:25-31);
+        to_gray=True additionally applies cvtColor(BGR2GRAY) to the resized frame (read_frame, optical_flow.py:34-46)."""
+        src = np.ascontiguousarray(src)
+        if src.dtype != np.uint8 or src.ndim not in (2, 3) or (src.ndim == 3 and src.shape[2] not in (1, 3)):
+            raise ValueError("src must be uint8 (H, W) or (H, W, 3)")
+        H, W = src.shape[:2]
+        cn = 1 if src.ndim == 2 else src.shape[2]
+        dW, dH = int(dsize[0]), int(dsize[1])
+        out = np.empty((dH, dW) if (src.ndim == 2 or to_gray) else (dH, dW, cn), np.uint8)
+        self._check(self._L.ofb_resize_u8_host(self._h, _ptr(src), W, H, cn, dW, dH, int(bool(to_gray)), _ptr(out)), "resize")
+        return out
+
+    @staticmethod
+    def _bgr_stack(frames, name):
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
+            raise ValueError("%s must be (n, H, W, 3) uint8" % name)
+        return frames
+
+    def shot_bgr(self, frames_bgr, dsize=None, want_bgr=True, want_magsum=False, want_flow=False, want_gray=False, **params):
+        """`shot` fed with the decoded BGR frames (n, H, W, 3): the optional cv2.resize to dsize = (w, h) and the gray
+        conversion run on the GPU, so each frame crosses PCIe once and is never touched by the host again."""
+        f = self._bgr_stack(frames_bgr, "frames_bgr")
+        if f.shape[0] < 2:
+            raise ValueError("need at least two frames")
+        n, H, W = f.shape[:3]
+        dW, dH = (W, H) if dsize is None else (int(dsize[0]), int(dsize[1]))
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        bgr = np.empty((n - 1, dH, dW, 3), np.uint8) if want_bgr else None
+        ms = np.zeros(n - 1, np.float32) if want_magsum else None
+        fl = np.empty((n - 1, dH, dW, 2), np.float32) if want_flow else None
+        gr = np.empty((n, dH, dW), np.uint8) if want_gray else None
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_shot_bgr_host(self._h, _ptr(f), n, W, H, 0 if dsize is None else dW, 0 if dsize is None else dH,
+                                              C.byref(prm), _ptr(bgr), _ptr(ms), _ptr(fl), _ptr(gr), C.byref(dev_ms)))
+        return {"bgr": bgr, "magsum": ms, "flow": fl, "gray": gr, "device_ms": float(dev_ms.value)}
+
+    def pairs_bgr(self, prev_bgr, next_bgr, dsize=None, want_bgr=False, want_magsum=True, want_flow=False, **params):
+        """`pairs` fed with decoded BGR frames; resize / gray conversion on the GPU (optical_flow.py:83-99 with read_frame)."""
+        a = self._bgr_stack(prev_bgr, "prev_bgr")
+        b = self._bgr_stack(next_bgr, "next_bgr")
+        if a.shape != b.shape or a.shape[0] < 1:
+            raise ValueError("prev_bgr / next_bgr must have the same shape (n>=1, H, W, 3)")
+        n, H, W = a.shape[:3]
+        dW, dH = (W, H) if dsize is None else (int(dsize[0]), int(dsize[1]))
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        bgr = np.empty((n, dH, dW, 3), np.uint8) if want_bgr else None
+        ms = np.zeros(n, np.float32) if want_magsum else None
+        fl = np.empty((n, dH, dW, 2), np.float32) if want_flow else None
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_pairs_bgr_host(self._h, _ptr(a), _ptr(b), n, W, H, 0 if dsize is None else dW,
+                                               0 if dsize is None else dH, C.byref(prm), _ptr(bgr), _ptr(ms), _ptr(fl), C.byref(dev_ms)))
+        return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
+
     # -- device-resident shot (bench: inputs already in HBM) -------------------------------------------
     def device_alloc(self, nbytes):
         p = self._L.ofb_device_alloc(self._h, int(nbytes))

@@ -19,8 +19,8 @@ OPTFLOW_FARNEBACK_GAUSSIAN = 256
 
 def build(force=False):
     """Compile the C oracle with gcc (oracle/Makefile)."""
-    src = os.path.join(_HERE, "farneback_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "preprocess_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -59,6 +59,8 @@ def lib():
         L.orc_sum_f32.argtypes = [fp, C.c_size_t]
         L.orc_sum_f32.restype = C.c_float
         L.orc_hsv2bgr_pixel.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_bgr2gray.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        L.orc_resize_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
         L.orc_viz.argtypes = [fp, C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]
         L.orc_sum_magnitude.argtypes = [fp, C.c_int, C.c_int]
         L.orc_sum_magnitude.restype = C.c_float
@@ -241,3 +243,24 @@ def sum_magnitude(flow):
     flow = _f32(flow)
     H, W = flow.shape[:2]
     return float(lib().orc_sum_magnitude(_f(flow), W, H))
+
+
+# ---- frame preprocessing (oracle/preprocess_oracle.c) -------------------------------------
+def bgr2gray(bgr):
+    """cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) for uint8 (optical_flow.py:44, visualize_optical_flow.py:31,35)."""
+    bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+    H, W = bgr.shape[:2]
+    out = np.empty((H, W), np.uint8)
+    lib().orc_bgr2gray(_u8(bgr), W, H, _u8(out))
+    return out
+
+
+def resize_u8(src, dsize):
+    """cv2.resize(src, (w, h)) with the default INTER_LINEAR for uint8, 1 or 3 channels (optical_flow.py:25-31)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    H, W = src.shape[:2]
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    dW, dH = int(dsize[0]), int(dsize[1])
+    out = np.empty((dH, dW) if src.ndim == 2 else (dH, dW, cn), np.uint8)
+    lib().orc_resize_u8(_u8(src), W, H, cn, _u8(out), dW, dH)
+    return out

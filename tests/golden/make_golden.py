@@ -37,6 +37,18 @@ CASES = {
 }
 
 
+# name: (source W, H, destination W, H, seed).  Destination heights follow optical_flow.py:27-29
+# (int(frame_width / (w / h))) where the case mimics --frame_width 129.
+PREPROCESS_CASES = {
+    "down_320x180_to_129x72": (320, 180, 129, 72, 31),        # the feature path's default regime
+    "down_odd_203x151_to_129x95": (203, 151, 129, 95, 32),
+    "half_128x96_to_64x48": (128, 96, 64, 48, 33),            # exact ratio 2
+    "up_100x60_to_129x77": (100, 60, 129, 77, 34),            # frame narrower than --frame_width
+    "same_129x72": (129, 72, 129, 72, 35),
+    "tiny_5x4_to_17x9": (5, 4, 17, 9, 36),
+}
+
+
 def main():
     for name, (W, H, seed, kw) in CASES.items():
         prev, nxt = synth.pair(W, H, seed)
@@ -69,6 +81,23 @@ def main():
     np.savez_compressed(os.path.join(HERE, "hsv2bgr_table.npz"), body=body, tail=tail,
                         cv2_version=np.array(cv2.__version__))
     print("hsv table: body/tail differ on %.1f%% of (H,V)" % (100 * (body != tail).any(-1).mean()))
+
+    # frame preprocessing either side of the hot path: cv2.resize (default INTER_LINEAR) of
+    # the decoded BGR frame, then cvtColor(BGR2GRAY) -- optical_flow.py:25-31, :42-44; visualize_optical_flow.py:31,35
+    pre = {}
+    for name, (sw, sh, dw, dh, seed) in PREPROCESS_CASES.items():
+        rng = np.random.default_rng(seed)
+        noise = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        smooth = cv2.GaussianBlur(noise, (0, 0), 2.5)
+        src = np.where(rng.random((sh, sw, 1)) < 0.5, noise, smooth).astype(np.uint8)     # hard and soft texture mixed
+        resized = cv2.resize(src, (dw, dh))
+        pre[name + "_src"] = src
+        pre[name + "_resized"] = resized
+        pre[name + "_gray"] = cv2.cvtColor(resized, cv2.COLOR_BGR2GRAY)
+        pre[name + "_gray_fullres"] = cv2.cvtColor(src, cv2.COLOR_BGR2GRAY)
+        pre[name + "_resized_c1"] = cv2.resize(src[..., 1].copy(), (dw, dh))
+        print("preprocess", name, src.shape, "->", resized.shape)
+    np.savez_compressed(os.path.join(HERE, "preprocess.npz"), cv2_version=np.array(cv2.__version__), **pre)
 
 
 if __name__ == "__main__":

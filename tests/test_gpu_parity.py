@@ -9,7 +9,9 @@ HSV picture within +-1 on >= 99.9 % of pixels.  Integer / byte results that have
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden, epe, EPE_MEAN_TOL, EPE_MAX_TOL
+import os
+
+from conftest import golden_cases, load_golden, epe, EPE_MEAN_TOL, EPE_MAX_TOL, GOLDEN_DIR
 
 pytestmark = pytest.mark.gpu
 
@@ -532,3 +534,54 @@ def test_native_library_is_what_ran(eng):
     assert "libofb200.so" in maps
     stats = eng.kernel_stats()
     assert stats.get("iter_fused", (0, 0))[0] > 0 and stats.get("polyexp_scale0", (0, 0))[0] > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# frame preprocessing on the GPU: integer algorithms, bit-exact
+# ------------------------------------------------------------------------------------------------
+def _preprocess_cases():
+    z = np.load(os.path.join(GOLDEN_DIR, "preprocess.npz"))
+    return z, sorted(k[:-len("_src")] for k in z.files if k.endswith("_src"))
+
+
+@pytest.mark.parametrize("name", _preprocess_cases()[1])
+def test_preprocess_matches_cv2_golden_bit_exactly(eng, name):
+    z, _ = _preprocess_cases()
+    src, resized, gray = z[name + "_src"], z[name + "_resized"], z[name + "_gray"]
+    dh, dw = resized.shape[:2]
+    assert np.array_equal(eng.resize(src, (dw, dh)), resized)
+    assert np.array_equal(eng.resize(src[..., 1].copy(), (dw, dh)), z[name + "_resized_c1"])
+    assert np.array_equal(eng.resize(src, (dw, dh), to_gray=True), gray)          # fused resize + gray
+    assert np.array_equal(eng.bgr_to_gray(resized), gray)
+    assert np.array_equal(eng.bgr_to_gray(src), z[name + "_gray_fullres"])
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 129, 72), (1280, 720, 129, 72), (640, 360, 320, 180), (333, 222, 129, 86),
+                                         (96, 64, 129, 86), (1920, 1080, 1920, 1080)])
+def test_preprocess_matches_oracle_at_video_sizes(eng, oracle, sw, sh, dw, dh):
+    rng = np.random.default_rng(sw * 7 + dw)
+    src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    ref = oracle.resize_u8(src, (dw, dh))
+    assert np.array_equal(eng.resize(src, (dw, dh)), ref)
+    assert np.array_equal(eng.resize(src, (dw, dh), to_gray=True), oracle.bgr2gray(ref))
+    assert np.array_equal(eng.bgr_to_gray(src), oracle.bgr2gray(src))
+
+
+def test_shot_bgr_equals_host_preprocessing_then_shot(eng, oracle):
+    """Feeding decoded BGR frames (resize + gray on the GPU) gives bit-identical pictures, sums and gray frames to
+    preprocessing with the oracle and feeding gray frames; both with and without the resize."""
+    rng = np.random.default_rng(77)
+    base = (rng.random((5, 120 + 16, 160 + 16, 3)) * 255).astype(np.uint8)
+    import scipy.ndimage as ndi
+    base = ndi.gaussian_filter(base.astype(np.float32), (0, 2, 2, 0))
+    base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+    frames = np.stack([base[0, i:i + 120, 2 * i:2 * i + 160] for i in range(5)])          # moving crop of one texture
+    for dsize in (None, (129, 96)):
+        gray = np.stack([oracle.bgr2gray(f if dsize is None else oracle.resize_u8(f, dsize)) for f in frames])
+        a = eng.shot_bgr(frames, dsize=dsize, want_bgr=True, want_magsum=True, want_gray=True)
+        b = eng.shot(gray, want_bgr=True, want_magsum=True)
+        assert np.array_equal(a["gray"], gray)
+        assert np.array_equal(a["bgr"], b["bgr"])
+        assert np.array_equal(a["magsum"], b["magsum"])
+        c = eng.pairs_bgr(frames[:-1], frames[1:], dsize=dsize, want_magsum=True)
+        assert np.array_equal(c["magsum"], b["magsum"])

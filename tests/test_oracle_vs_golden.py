@@ -81,3 +81,33 @@ def test_oracle_rejects_pyr_scale_ge_1(oracle):
     p = dict(g["kw"]); p["pyr_scale"] = 1.0
     with pytest.raises(ValueError):
         oracle.farneback(g["prev"], g["next"], None, **p)
+
+
+# ---- frame preprocessing: integer algorithms, bit-exact -------------------------------------
+def _preprocess_golden():
+    z = np.load(GOLDEN_DIR + "/preprocess.npz")
+    names = sorted(k[:-len("_src")] for k in z.files if k.endswith("_src"))
+    return z, names
+
+
+@pytest.mark.parametrize("name", _preprocess_golden()[1])
+def test_preprocess_oracle_is_bit_exact_against_cv2(oracle, name):
+    z, _ = _preprocess_golden()
+    src, resized, gray = z[name + "_src"], z[name + "_resized"], z[name + "_gray"]
+    dh, dw = resized.shape[:2]
+    assert np.array_equal(oracle.resize_u8(src, (dw, dh)), resized)                       # cv2.resize, 3 channels
+    assert np.array_equal(oracle.resize_u8(src[..., 1].copy(), (dw, dh)), z[name + "_resized_c1"])   # 1 channel
+    assert np.array_equal(oracle.bgr2gray(resized), gray)                                 # cvtColor(BGR2GRAY)
+    assert np.array_equal(oracle.bgr2gray(src), z[name + "_gray_fullres"])
+
+
+def test_bgr2gray_oracle_exhaustive_channels(oracle):
+    """Every value of each channel against the closed form, and the weights sum to one (gray of a gray pixel is itself)."""
+    v = np.arange(256, dtype=np.uint8)
+    for c in range(3):
+        px = np.zeros((1, 256, 3), np.uint8)
+        px[0, :, c] = v
+        w = (3735, 19235, 9798)[c]
+        assert np.array_equal(oracle.bgr2gray(px)[0], ((v.astype(np.int64) * w + 16384) >> 15).astype(np.uint8))
+    g = np.repeat(v[None, :, None], 3, axis=2)
+    assert np.array_equal(oracle.bgr2gray(g)[0], v)
