@@ -10,9 +10,11 @@ pair's Farneback flow to the summed magnitude, averages the windows covering eac
 (/root/reference/optical_flow.py:69-168).
 
 The per-pair hot path (calculate_optical_flow, optical_flow.py:49-66: cv2.calcOpticalFlowFarneback ->
-cartToPolar -> np.sum) does not run on the CPU here: all windows of a video are decoded first, then submitted
-to the GPU engine as one batch of independent pairs (optical_flow_b200.Farneback.pairs -> C-ABI ofb_pairs_host).
-Decoding, resizing and BGR->gray stay on the host with cv2, exactly as the reference does them.
+cartToPolar -> np.sum) does not run on the CPU here, and neither does read_frame's resize + BGR->gray (:25-46): the
+decoded BGR frames of PAIRS_PER_SUBMISSION windows at a time go to the GPU engine as one batch of independent pairs
+(optical_flow_b200.Farneback.pairs_bgr -> C-ABI ofb_pairs_bgr_host; the resize and the gray conversion are bit-exact
+re-implementations of cv2's).  Decoding stays with cv2; a frame that lies just ahead of the decoder is reached by
+decoding forward instead of a seek (optical_flow_b200/video.py).
 """
 import argparse
 import logging
@@ -23,10 +25,12 @@ import numpy as np
 from tqdm import tqdm
 
 import optical_flow_b200 as ofb
+from optical_flow_b200.video import FrameReader
 
 EXTRACTOR = "opticalflow"
 VERSION = '20201209'      # kept equal to the reference's, so existing .done files stay valid
 STANDALONE = True         # True: write .done files; False: always recompute and never write them
+PAIRS_PER_SUBMISSION = 32 # decoded frame pairs handed to the GPU at a time (bounds host memory on long videos)
 
 logger = logging.getLogger(__name__)
 logging.basicConfig(level=logging.INFO)
@@ -36,28 +40,18 @@ logger.addHandler(_handler)
 logger.propagate = False
 
 
-def resize_frame(frame, frame_width):
-    """Keep the aspect ratio, target width `frame_width` (optical_flow.py:25-31; default bilinear cv2.resize)."""
+def resized_size(frame, frame_width):
+    """Target (width, height) of resize_frame (optical_flow.py:25-31): keep the aspect ratio, width `frame_width`."""
     h, w = frame.shape[0], frame.shape[1]
-    frame_height = int(frame_width / (w / h))
-    return cv2.resize(frame, (frame_width, frame_height))
+    return frame_width, int(frame_width / (w / h))
 
 
-def read_frame(vid, timestamp, frame_width):
-    """Seek, decode, optionally resize, convert to gray (optical_flow.py:34-46)."""
-    vid.set(cv2.CAP_PROP_POS_FRAMES, timestamp)
-    ok, frame = vid.read()
-    if not ok:
-        return ok, None
-    if frame_width:
-        frame = resize_frame(frame, frame_width)
-    return ok, cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
-
-
-def calculate_optical_flow_batch(starts, ends, engine=None):
-    """The batched counterpart of calculate_optical_flow (optical_flow.py:49-66): one summed magnitude per pair."""
+def calculate_optical_flow_batch(starts, ends, frame_width, engine=None):
+    """The batched counterpart of read_frame's preprocessing + calculate_optical_flow (optical_flow.py:25-66) for
+    decoded BGR frames: resize to `frame_width` (if set), BGR->gray, Farneback, one summed magnitude per pair."""
     eng = engine or ofb.default_engine()
-    res = eng.pairs(np.stack(starts), np.stack(ends), want_magsum=True, **ofb.REFERENCE_PARAMS)
+    dsize = resized_size(starts[0], frame_width) if frame_width else None
+    res = eng.pairs_bgr(np.stack(starts), np.stack(ends), dsize=dsize, want_magsum=True, **ofb.REFERENCE_PARAMS)
     return res["magsum"]
 
 
@@ -73,23 +67,31 @@ def get_optical_flow(v_path, frame_width, step_size, window_size, engine=None):
     half = int(int(fps * window_size / 1000) / 2.)
     windows = [(max(0, c - half), min(tot_frames - 1, c + half)) for c in range(0, tot_frames, step)]
 
-    # host: decode every window's two frames; the first unreadable frame ends the video (optical_flow.py:87-96)
-    spans, starts, ends = [], [], []
+    # host: decode every window's two frames; the first unreadable frame ends the video (optical_flow.py:87-96).
+    # GPU: PAIRS_PER_SUBMISSION windows per batch.
+    reader = FrameReader(vid)
+    mags, spans, starts, ends = [], [], [], []
+
+    def flush():
+        if spans:
+            sums = calculate_optical_flow_batch(starts, ends, frame_width, engine)
+            mags.extend((s, e, m) for (s, e), m in zip(spans, sums))
+            del spans[:], starts[:], ends[:]
+
     for first, last in windows:
-        ok, a = read_frame(vid, first, frame_width)
+        ok, a = reader.read_at(first)
         if not ok or a is None:
             break
-        ok, b = read_frame(vid, last, frame_width)
+        ok, b = reader.read_at(last)
         if not ok or b is None:
             break
         spans.append((first, last)); starts.append(a); ends.append(b)
-    if not spans:
+        if len(spans) >= PAIRS_PER_SUBMISSION:
+            flush()
+    flush()
+    if not mags:
         raise Exception('Unable to extract the optical flow, no frames where found.')
     vid.release()
-
-    # GPU: all pairs of the video in one batch
-    sums = calculate_optical_flow_batch(starts, ends, engine)
-    mags = [(s, e, m) for (s, e), m in zip(spans, sums)]
 
     agg = []
     for pos in range(0, tot_frames, step):

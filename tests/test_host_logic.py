@@ -9,7 +9,7 @@ import pytest
 import optical_flow_b200 as ofb
 from optical_flow_b200 import _lib
 from optical_flow_b200.engine import validate_call
-from conftest import ROOT
+from conftest import ROOT, GOLDEN_DIR
 
 
 def test_library_loads_and_exports_every_declared_symbol():
@@ -128,3 +128,49 @@ def test_shard_shots_balanced_and_complete():
         assert max(loads) - min(loads) <= max(lengths)
     parts = ofb.shard_shots([1000], 4)
     assert sorted(p for r in parts for p in r) == [(0, 0, 250), (0, 250, 250), (0, 500, 250), (0, 750, 250)]
+
+
+# ---- host-side video helpers of the entry-point scripts ------------------------------
+def test_frame_reader_returns_the_frames_a_seek_per_frame_returns():
+    """Decoding forward to a frame that lies ahead gives the frame `set(CAP_PROP_POS_FRAMES); read()` gives, for the
+    access patterns of both scripts (float positions, window pairs, a backward jump) on the golden video."""
+    cv2 = pytest.importorskip("cv2")
+    from optical_flow_b200.video import FrameReader
+    path = os.path.join(GOLDEN_DIR, "scripts", "vidA.mp4")
+    patterns = {
+        "visualize": [0.0, 7.0, 14.0, 21.0, 28.0, 35.0, 42.0],                 # fps*start/1000 + k*int(fps*0.3)
+        "float": [2.5, 9.5, 16.5, 23.5],
+        "windows": [0, 3, 4, 10, 11, 17, 18, 24, 25, 31, 32, 38, 39, 45, 46, 47],
+        "backward": [10, 20, 5, 6, 30, 30, 31],
+        "past_end": [40, 47, 48, 3],
+    }
+    for name, positions in patterns.items():
+        ref = cv2.VideoCapture(path)
+        want = []
+        for p in positions:
+            ref.set(cv2.CAP_PROP_POS_FRAMES, p)
+            want.append(ref.read())
+        ref.release()
+        vid = cv2.VideoCapture(path)
+        rd = FrameReader(vid)
+        got = [rd.read_at(p) for p in positions]
+        vid.release()
+        for p, (ok_w, f_w), (ok_g, f_g) in zip(positions, want, got):
+            assert ok_w == ok_g, (name, p)
+            if ok_w:
+                assert np.array_equal(f_w, f_g), (name, p)
+        if name in ("visualize", "windows"):
+            assert rd.seeks == 1 and rd.grabs > 0, (name, rd.seeks, rd.grabs)      # one seek, then forward decoding
+
+
+def test_jpeg_writer_writes_the_same_bytes_as_imwrite(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from optical_flow_b200.video import JpegWriter
+    rng = np.random.default_rng(0)
+    imgs = [cv2.GaussianBlur(rng.integers(0, 256, (90, 120, 3), dtype=np.uint8), (0, 0), 1.5) for _ in range(6)]
+    with JpegWriter(workers=3) as w:
+        for i, im in enumerate(imgs):
+            w.imwrite(str(tmp_path / ("a%d.jpeg" % i)), im)
+    for i, im in enumerate(imgs):
+        cv2.imwrite(str(tmp_path / ("b%d.jpeg" % i)), im)
+        assert (tmp_path / ("a%d.jpeg" % i)).read_bytes() == (tmp_path / ("b%d.jpeg" % i)).read_bytes()

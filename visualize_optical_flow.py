@@ -7,11 +7,13 @@ It writes exactly the files the reference writes (/root/reference/visualize_opti
 sampled frame after the first, `flow_<ms>.jpeg` (the HSV-coded Farneback flow against the previous sampled frame)
 and `source_<ms>.jpeg` (the frame itself), sampling every 300 ms between shot_begin and shot_end.
 
-What differs is only WHERE the hot path runs: the reference calls cv2.calcOpticalFlowFarneback + cartToPolar +
-normalize + cvtColor once per pair in a Python loop (:37-55); here all sampled frames of the shot are collected
-first and handed to the GPU engine as ONE shot (optical_flow_b200.Farneback.shot -> C-ABI ofb_shot_host), which
-expands each frame once, batches the pairs, and returns the BGR pictures.  Decoding (cv2.VideoCapture), the
-BGR->gray conversion and JPEG encoding stay on the host, as in the reference.
+What differs is only WHERE the hot path runs: the reference calls cvtColor(BGR2GRAY) + cv2.calcOpticalFlowFarneback +
+cartToPolar + normalize + cvtColor once per pair in a Python loop (:31-55); here the sampled BGR frames of the shot are
+handed to the GPU engine as ONE shot (optical_flow_b200.Farneback.shot_bgr -> C-ABI ofb_shot_bgr_host), which converts
+to gray on the device, expands each frame once, batches the pairs, and returns the BGR pictures.  Decoding
+(cv2.VideoCapture) and JPEG encoding stay with cv2 on the host, as in the reference; frames ahead of the decoder are
+reached by decoding forward instead of a seek per frame, and the JPEGs are encoded by a small thread pool
+(optical_flow_b200/video.py).
 """
 import argparse
 import os
@@ -20,8 +22,10 @@ import cv2
 import numpy as np
 
 import optical_flow_b200 as ofb
+from optical_flow_b200.video import FrameReader, JpegWriter
 
 STEP_SIZE = 300     # ms between sampled frames (reference: module constant of the same name)
+MAX_FRAMES = 96     # decoded frames per GPU submission
 
 
 def sample_shot(v_path, start_ms, end_ms):
@@ -34,9 +38,9 @@ def sample_shot(v_path, start_ms, end_ms):
     last = int(fps * end_ms / 1000)
     stride = int(fps * STEP_SIZE / 1000)
     positions, frames = [], []
+    reader = FrameReader(vid)
     while pos < last:
-        vid.set(cv2.CAP_PROP_POS_FRAMES, pos)
-        ok, bgr = vid.read()
+        ok, bgr = reader.read_at(pos)           # == vid.set(CAP_PROP_POS_FRAMES, pos); vid.read()
         if not ok:
             break
         positions.append(pos)
@@ -54,17 +58,21 @@ def get_optical_flow(v_path, images_path, start_ms, end_ms, engine=None):
     positions, frames, fps = sample_shot(v_path, start_ms, end_ms)
     if len(frames) < 2:
         return []
-    gray = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in frames])
     eng = engine or ofb.default_engine()
-    pictures = eng.shot(gray, want_bgr=True, **ofb.REFERENCE_PARAMS)["bgr"]     # hot path: one GPU submission
     written = []
-    for k in range(1, len(frames)):
-        stamp = str(int(positions[k] / fps * 1000))
-        path_flow = os.path.join(images_path, "flow_" + stamp + ".jpeg")
-        path_source = os.path.join(images_path, "source_" + stamp + ".jpeg")
-        cv2.imwrite(path_flow, pictures[k - 1])
-        cv2.imwrite(path_source, frames[k])
-        written += [path_flow, path_source]
+    with JpegWriter() as out:
+        # hot path: one GPU submission per chunk of consecutive frames (chunks share their boundary frame, so a long
+        # shot never holds more than MAX_FRAMES decoded frames in one array; results do not depend on the chunking)
+        for c0 in range(0, len(frames) - 1, MAX_FRAMES - 1):
+            chunk = frames[c0:c0 + MAX_FRAMES]
+            pictures = eng.shot_bgr(np.stack(chunk), want_bgr=True, **ofb.REFERENCE_PARAMS)["bgr"]
+            for k in range(1, len(chunk)):
+                stamp = str(int(positions[c0 + k] / fps * 1000))
+                path_flow = os.path.join(images_path, "flow_" + stamp + ".jpeg")
+                path_source = os.path.join(images_path, "source_" + stamp + ".jpeg")
+                out.imwrite(path_flow, pictures[k - 1])
+                out.imwrite(path_source, chunk[k])
+                written += [path_flow, path_source]
     return written
 
 
