@@ -17,6 +17,8 @@ reached by decoding forward instead of a seek per frame, and the JPEGs are encod
 """
 import argparse
 import os
+import queue
+import threading
 
 import cv2
 import numpy as np
@@ -25,54 +27,69 @@ import optical_flow_b200 as ofb
 from optical_flow_b200.video import FrameReader, JpegWriter
 
 STEP_SIZE = 300     # ms between sampled frames (reference: module constant of the same name)
-MAX_FRAMES = 96     # decoded frames per GPU submission
+MAX_FRAMES = 17     # decoded frames per GPU submission (16 pairs)
 
 
 def sample_shot(v_path, start_ms, end_ms):
-    """Frames the reference's loop would visit (visualize_optical_flow.py:14-27, :63): positions start at the
-    *float* fps*start_ms/1000 and advance by int(fps*STEP_SIZE/1000); stops at the first unreadable frame.
-    Returns (positions, BGR frames, fps)."""
+    """Generator over the frames the reference's loop would visit (visualize_optical_flow.py:14-27, :63): positions
+    start at the *float* fps*start_ms/1000 and advance by int(fps*STEP_SIZE/1000); it stops at the first unreadable
+    frame.  Yields (position, BGR frame, fps)."""
     vid = cv2.VideoCapture(v_path)
     fps = vid.get(cv2.CAP_PROP_FPS)
     pos = fps * start_ms / 1000
     last = int(fps * end_ms / 1000)
     stride = int(fps * STEP_SIZE / 1000)
-    positions, frames = [], []
     reader = FrameReader(vid)
-    while pos < last:
-        ok, bgr = reader.read_at(pos)           # == vid.set(CAP_PROP_POS_FRAMES, pos); vid.read()
-        if not ok:
-            break
-        positions.append(pos)
-        frames.append(bgr)
-        if stride <= 0:          # the reference would spin forever on this input; one frame is all it can mean
-            break
-        pos += stride
-    vid.release()
-    return positions, frames, fps
+    try:
+        while pos < last:
+            ok, bgr = reader.read_at(pos)           # == vid.set(CAP_PROP_POS_FRAMES, pos); vid.read()
+            if not ok:
+                break
+            yield pos, bgr, fps
+            if stride <= 0:          # the reference would spin forever on this input; one frame is all it can mean
+                break
+            pos += stride
+    finally:
+        vid.release()
 
 
 def get_optical_flow(v_path, images_path, start_ms, end_ms, engine=None):
-    """Same signature and artefacts as the reference's get_optical_flow (visualize_optical_flow.py:9)."""
+    """Same signature and artefacts as the reference's get_optical_flow (visualize_optical_flow.py:9).
+
+    Streaming: a decoder thread runs ahead of the GPU (cv2 releases the GIL while decoding); every MAX_FRAMES
+    consecutive sampled frames are one GPU submission (chunks share their boundary frame; results do not depend on
+    the chunking), and the JPEGs of a finished chunk are encoded by the writer pool while the next chunk is decoded."""
     os.makedirs(images_path, exist_ok=True)
-    positions, frames, fps = sample_shot(v_path, start_ms, end_ms)
-    if len(frames) < 2:
-        return []
     eng = engine or ofb.default_engine()
     written = []
+    frames_q = queue.Queue(maxsize=2 * MAX_FRAMES)
+
+    def decode():
+        try:
+            for item in sample_shot(v_path, start_ms, end_ms):
+                frames_q.put(item)
+        finally:
+            frames_q.put(None)
+
+    threading.Thread(target=decode, daemon=True).start()
     with JpegWriter() as out:
-        # hot path: one GPU submission per chunk of consecutive frames (chunks share their boundary frame, so a long
-        # shot never holds more than MAX_FRAMES decoded frames in one array; results do not depend on the chunking)
-        for c0 in range(0, len(frames) - 1, MAX_FRAMES - 1):
-            chunk = frames[c0:c0 + MAX_FRAMES]
-            pictures = eng.shot_bgr(np.stack(chunk), want_bgr=True, **ofb.REFERENCE_PARAMS)["bgr"]
-            for k in range(1, len(chunk)):
-                stamp = str(int(positions[c0 + k] / fps * 1000))
-                path_flow = os.path.join(images_path, "flow_" + stamp + ".jpeg")
-                path_source = os.path.join(images_path, "source_" + stamp + ".jpeg")
-                out.imwrite(path_flow, pictures[k - 1])
-                out.imwrite(path_source, chunk[k])
-                written += [path_flow, path_source]
+        chunk, positions, fps, done = [], [], 0.0, False
+        while not done:
+            item = frames_q.get()
+            if item is None:
+                done = True
+            else:
+                positions.append(item[0]); chunk.append(item[1]); fps = item[2]
+            if len(chunk) >= 2 and (done or len(chunk) == MAX_FRAMES):
+                pictures = eng.shot_bgr(np.stack(chunk), want_bgr=True, **ofb.REFERENCE_PARAMS)["bgr"]    # hot path
+                for k in range(1, len(chunk)):
+                    stamp = str(int(positions[k] / fps * 1000))
+                    path_flow = os.path.join(images_path, "flow_" + stamp + ".jpeg")
+                    path_source = os.path.join(images_path, "source_" + stamp + ".jpeg")
+                    out.imwrite(path_flow, pictures[k - 1])
+                    out.imwrite(path_source, chunk[k])
+                    written += [path_flow, path_source]
+                chunk, positions = chunk[-1:], positions[-1:]
     return written
 
 
