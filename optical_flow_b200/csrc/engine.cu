@@ -518,7 +518,7 @@ int shot_batch(const ofb_context* ctx, int W, int H, int n_pairs)
     int b = ctx->batch;
     if (b <= 0) {
         double px = (double)W * H;
-        b = (int)std::ceil(32.0e6 / px);
+        b = (int)std::ceil(48.0e6 / px);
         b = std::max(4, std::min(b, MAX_BATCH));
     }
     return std::max(1, std::min(b, std::min(n_pairs, MAX_BATCH)));
@@ -966,7 +966,20 @@ static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames,
     }
     Launch L{sc, &ctx->prof};
     const int n_pairs = n_frames - 1;
-    const int n_chunks = (n_pairs + B - 1) / B;
+    // Chunk schedule: full chunks of B pairs, but a long shot starts and ends with short ones (B/4, B/2, ..., B/2, B/4):
+    // the first upload and the last download are the only copies that nothing overlaps, so they are kept small.
+    std::vector<int> cstart;                                              // first pair of every chunk, then n_pairs
+    {
+        std::vector<int> head, tail;
+        if (n_pairs >= 4 * B && B >= 8) { head = {B / 4, B / 2}; tail = {B / 2, B / 4}; }
+        int t = 0, tail_sum = 0;
+        for (int v : tail) tail_sum += v;
+        for (int v : head) { cstart.push_back(t); t += v; }
+        while (n_pairs - tail_sum - t > 0) { cstart.push_back(t); t += std::min(B, n_pairs - tail_sum - t); }
+        for (int v : tail) { cstart.push_back(t); t += v; }
+        cstart.push_back(n_pairs);
+    }
+    const int n_chunks = (int)cstart.size() - 1;
 
     CU(cudaEventRecord(ctx->ev_t0, su));
     // Uploads run ahead on s_h2d (frames of chunk c go to fstage[c & 1]), results drain on s_d2h
@@ -974,7 +987,7 @@ static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames,
     // the events it needs, so H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c.
     CU(cudaMemcpyAsync(from_bgr ? bs0 : pl.f0, frames, sn, cudaMemcpyHostToDevice, su));
     auto upload = [&](int c) -> int {
-        const int t0 = c * B, b = std::min(B, n_pairs - t0), par = c & 1;
+        const int t0 = cstart[c], b = cstart[c + 1] - t0, par = c & 1;
         if (c >= 2) CU(cudaStreamWaitEvent(su, ctx->ev_frame_free[par], 0));
         CU(cudaMemcpyAsync(from_bgr ? bs[par] : pl.fstage[par], frames + (size_t)(t0 + 1) * sn, (size_t)b * sn, cudaMemcpyHostToDevice, su));
         CU(cudaEventRecord(ctx->ev_h2d[par], su));
@@ -982,7 +995,7 @@ static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames,
     };
     if (int rc = upload(0)) return rc;
     for (int c = 0; c < n_chunks; c++) {
-        const int t0 = c * B, b = std::min(B, n_pairs - t0), par = c & 1;
+        const int t0 = cstart[c], b = cstart[c + 1] - t0, par = c & 1;
         if (c + 1 < n_chunks) if (int rc = upload(c + 1)) return rc;
         CU(cudaStreamWaitEvent(sc, ctx->ev_h2d[par], 0));
         if (from_bgr) {
