@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "1080p Farneback frame-pairs/sec"
 UNIT = "pairs/s"
+TRAFFIC_JSON = "r1g_traffic.json"      # measured DRAM bytes per pair and kernel (tools/ncu_traffic.py) of the current kernels
 PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
 
 # algorithmic HBM bytes per pixel of a launch, per kernel (SURVEY.md 8d stage model)
@@ -321,10 +322,10 @@ def run_ours(args, rank, local_rank, world):
             # measured DRAM bytes of the same kernel from the committed `ncu --set full` capture, per launch like `achieved`
             traffic, traffic_src = None, None
             try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))
+                tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_JSON)))
                 per_pair = tj["kernels"][dom[0]]["dram_bytes_per_pair"]
                 traffic = round(per_pair * P / dom[1]["launches"], 1) if (W, H) == (1920, 1080) else None
-                traffic_src = "profiles/r1d_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)"
+                traffic_src = "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)" % TRAFFIC_JSON
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",

@@ -3,8 +3,10 @@ import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, data = rows[0], rows[2:]
+hdr, units, data = rows[0], rows[1], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}
+TO_MB = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+TO_US = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 cols = [("dur_us", "gpu__time_duration.sum"), ("dramR_MB", "dram__bytes_read.sum"), ("dramW_MB", "dram__bytes_write.sum"),
         ("dram%", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         ("sm%", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
@@ -32,5 +34,9 @@ for d in data:
             vals.append("     n/a"); continue
         if c == "inst_M":
             v /= 1e6
+        elif c.endswith("_MB"):
+            v *= TO_MB.get(units[idx[m]], 1.0)
+        elif c == "dur_us":
+            v *= TO_US.get(units[idx[m]], 1.0)
         vals.append("%8.2f" % v)
     print("%-28s %-14s " % (name, d[idx["Grid Size"]].replace(" ", "")) + " ".join(vals))

@@ -9,13 +9,16 @@ import csv
 import json
 import sys
 
-FAMILY = [("k_polyexp2<(int)5, (int)1>", "polyexp_scale0"), ("k_polyexp2", "polyexp_level"), ("k_pyr_vf", "pyr_v_u8"),
-          ("k_pyr_hf", "pyr_h"), ("k_pyr_h", "pyr_h_u8"), ("k_pyr_v", "pyr_v"), ("k_um0<(int)0>", "um0_zero"),
-          ("k_um0<(int)2>", "um0_upsample"), ("k_um0<(int)1>", "um0_flow"),
-          ("(bool)1, (int)1, (bool)0>", "iter_fused"), ("(bool)0, (int)1, (bool)0>", "iter_last"),
-          ("(bool)1, (int)1, (bool)1>", "iter_fused_gauss"), ("(bool)0, (int)1, (bool)1>", "iter_last_gauss"),
-          ("k_flow_to_bgr", "flow_to_bgr_v4"), ("k_minmax_reset", "minmax_reset"), ("k_minmax", "minmax_mag"),
-          ("k_bgr2gray", "bgr2gray"), ("k_resize_u8", "resize_u8")]
+import re
+
+# (regex on ncu's demangled kernel name, family) -- first match wins
+FAMILY = [(r"k_polyexp2<\d+, [12]>", "polyexp_scale0"), (r"k_polyexp2<", "polyexp_level"), (r"k_pyr_vf<", "pyr_v_u8"),
+          (r"k_pyr_hf<", "pyr_h"), (r"k_pyr_h", "pyr_h_u8"), (r"k_pyr_v", "pyr_v"), (r"k_um0<0>", "um0_zero"),
+          (r"k_um0<2>", "um0_upsample"), (r"k_um0<1>", "um0_flow"),
+          (r"k_iter<\d+, 1, \d+, 0>", "iter_fused"), (r"k_iter<\d+, 0, \d+, 0>", "iter_last"),
+          (r"k_iter<\d+, 1, \d+, 1>", "iter_fused_gauss"), (r"k_iter<\d+, 0, \d+, 1>", "iter_last_gauss"),
+          (r"k_flow_to_bgr", "flow_to_bgr_v4"), (r"k_minmax_reset", "minmax_reset"), (r"k_minmax", "minmax_mag"),
+          (r"k_bgr2gray", "bgr2gray"), (r"k_resize_u8", "resize_u8")]
 
 
 def unit_scale(u):
@@ -30,7 +33,8 @@ def main():
     out = {}
     for d in data:
         name = d[ix["Kernel Name"]]
-        fam = next((f for key, f in FAMILY if key in name), name[:40])
+        name = name.replace("(int)", "").replace("(bool)", "")
+        fam = next((f for key, f in FAMILY if re.search(key, name)), name[:40])
         def val(m):
             return float(d[ix[m]].replace(",", "")) * unit_scale(units[ix[m]])
         e = out.setdefault(fam, {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "ncu_us": 0.0})
