@@ -111,3 +111,19 @@ def test_bgr2gray_oracle_exhaustive_channels(oracle):
         assert np.array_equal(oracle.bgr2gray(px)[0], ((v.astype(np.int64) * w + 16384) >> 15).astype(np.uint8))
     g = np.repeat(v[None, :, None], 3, axis=2)
     assert np.array_equal(oracle.bgr2gray(g)[0], v)
+
+
+def test_preprocess_oracle_fuzz_against_installed_cv2(oracle):
+    """When cv2 is importable (this container, the GPU box): random geometries, up- and down-scaling, 1 and 3 channels."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2024)
+    for _ in range(40):
+        sw, sh = int(rng.integers(2, 300)), int(rng.integers(2, 200))
+        dw, dh = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+        cn = int(rng.choice([1, 3]))
+        src = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+        if cn == 1:
+            src = src[..., 0].copy()
+        assert np.array_equal(oracle.resize_u8(src, (dw, dh)), cv2.resize(src, (dw, dh))), (sw, sh, dw, dh, cn)
+        if cn == 3:
+            assert np.array_equal(oracle.bgr2gray(src), cv2.cvtColor(src, cv2.COLOR_BGR2GRAY))
