@@ -201,8 +201,8 @@ k_polyexp2(PolyArgs a)
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const unsigned char* srcb = (const unsigned char*)a.src + (size_t)z * a.src_item;
 
-    // Vertical pass, column-thread form: thread = (patch column px, row group g); group g owns output rows
-    // 5g .. 5g+5 (rows 5 and 10 are produced twice with identical values).  The thread pulls its 6+2N input values
+    // Vertical pass, column-thread form: thread = (patch column px, row group g); group 0 owns output rows 0..5,
+    // groups 1 and 2 rows 5g+1 .. 5g+5 (every group holds the inputs of six rows; g > 0 skips its first).  The thread pulls its 6+2N input values
     // straight into registers -- from global memory (SRC 0) or from the row-blurred patch (SRC 1, interior tiles), in
     // which case the column pass of the pre-blur is applied on the fly -- so the level image never sits in shared
     // memory and two block-wide passes (and their barriers) disappear.  Same arithmetic, same order as the tiled form.
@@ -211,6 +211,7 @@ k_polyexp2(PolyArgs a)
     auto vertical_from = [&](const float (&b)[VR + 2 * N], int g, int px) {
 #pragma unroll
         for (int o = 0; o < VR; o++) {
+            if (o == 0 && g > 0) continue;                   // row 5g belongs to group g-1
             const int cidx = o + N;
             float r0 = b[cidx] * a.g[0], r1 = 0.f, r2 = 0.f;
 #pragma unroll
