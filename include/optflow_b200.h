@@ -162,7 +162,10 @@ int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, in
  *   "profile"          1 = bracket every kernel launch with CUDA events on the launching stream
  *   "batch"            pairs per launch inside a shot (0 = chosen from the frame size)
  *   "batch_scale0"     pairs per launch at scale 0 (0 = same as batch)
- *   "iter_prefetch"    1 (default) = software L2 prefetch in the iteration kernel */
+ *   "iter_prefetch"    1 (default) = software L2 prefetch in the iteration kernel
+ *   "polyexp_tma"      1 = scale-0 polynomial expansion as a persistent grid whose halo tiles are staged by TMA
+ *                      (cp.async.bulk.tensor + mbarrier, double-buffered); bit-identical results, measured slower
+ *                      than the default one-tile-per-CTA kernel on B200, so off by default */
 int ofb_set_option(ofb_context* ctx, const char* name, int value);
 
 typedef struct ofb_kernel_stat {

@@ -152,6 +152,7 @@ void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const Po
 // batched, unrolled variant: src_kind 0 = level image (f32), 1 = u8 frame + fused [1/4 1/2 1/4]^2 pre-blur
 // (scale 0), 2 = f32 frame + the same pre-blur.  Returns false when poly_n has no unrolled instance.
 bool polyexp2_supported(int n);
+void set_polyexp_tma(int v);            // 1 = scale-0 polyexp as a persistent grid with TMA-staged halo tiles
 void launch_polyexp2(Launch& L, int src_kind, const PolyArgs& a, int batch);
 
 // matrices.cu -- A.2 and A.8

@@ -1326,6 +1326,7 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!strcmp(name, "alt_order")) { ctx->alt_order = value != 0; return OFB_OK; }
     if (!strcmp(name, "iter_ilp")) { set_iter_ilp(value); return OFB_OK; }
     if (!strcmp(name, "iter_prefetch")) { set_iter_prefetch(value); return OFB_OK; }
+    if (!strcmp(name, "polyexp_tma")) { set_polyexp_tma(value); return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "profile")) {

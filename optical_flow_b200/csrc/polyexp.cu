@@ -14,6 +14,9 @@
 // Roofline: reads 4 B/px (+halo from L2), writes 20 B/px -> HBM-bound; algorithmic bytes 24 B/px.
 #include "common.cuh"
 #include "launch.cuh"
+#include <cuda.h>          // CUtensorMap and its enums only; the encoder is fetched through cudaGetDriverEntryPoint
+#include <algorithm>
+
 
 namespace ofb {
 
@@ -181,24 +184,26 @@ void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const Po
 // keeps the 16 rows of a half-warp on distinct bank pairs, and each thread re-uses its 4+2N-wide
 // register window for 4 outputs.
 // ------------------------------------------------------------------------------------------------
+// One 64 x 16 tile of frame z.  `staged_off` (SRC 1 only): byte offset inside pe_smem of the tile's raw u8 patch -- rows
+// y0-N-1 .. y0+TH+N, columns from x0-8 on, PE_STAGE_PITCH bytes per row -- when TMA has already put it in shared
+// memory (k_polyexp2_tma), or -1: the patch is read from global memory.  All barriers are block-uniform.
+constexpr int PE_STAGE_PITCH = 64 + 32;      // TMA boxes start at x0-16: the innermost coordinate must be 16-byte aligned
 template <int N, int SRC>
-__global__ void __launch_bounds__(256, 4)
-k_polyexp2(PolyArgs a)
+__device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_smem, const int x0, const int y0, const int z,
+                                        const int staged_off)
 {
     constexpr int TW = 64, TH = 16;
     constexpr int PW = TW + 2 * N, PH = TH + 2 * N;
     constexpr int RP = (PW | 1);                       // odd pitch (in doubles) of the vertical-pass results
     constexpr int RAWW = PW + 2, RAWH = PH + 2;
-    extern __shared__ __align__(16) unsigned char pe_smem[];
     double* sR0 = reinterpret_cast<double*>(pe_smem);  // TH x RP each
     double* sR1 = sR0 + TH * RP;
     double* sR2 = sR1 + TH * RP;
     float* sI = reinterpret_cast<float*>(sR2 + TH * RP);        // PH x PW   (SRC != 0: aliases the raw patch)
     float* sHB = sI + RAWH * RAWW;                                // RAWH x PW (SRC != 0 only)
 
-    const int tid = threadIdx.x, z = blockIdx.z;
+    const int tid = threadIdx.x;
     const int W = a.W, H = a.H;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const unsigned char* srcb = (const unsigned char*)a.src + (size_t)z * a.src_item;
 
     // Vertical pass, column-thread form: thread = (patch column px, row group g); group 0 owns output rows 0..5,
@@ -261,16 +266,30 @@ k_polyexp2(PolyArgs a)
             float* sHBf = sI;
             if (xin) {
                 uchar4 q[NIT]; unsigned char lb[NIT], rb[NIT];
+                if (staged_off >= 0 && yin) {            // shared-memory loads (the compiler sees the address space)
 #pragma unroll
-                for (int k = 0; k < NIT; k++) {          // all loads of the thread in flight before the first use
-                    const int i = tid + 256 * k;
-                    if (i < RAWH * NVEC) {
-                        const int j = i / NVEC, v = i - j * NVEC;
-                        const int fy = yin ? uby + j : reflect101(uby + j, H);
-                        const unsigned char* p = srcb + (size_t)fy * a.src_pitch + (x0 - 8) + 4 * v;
-                        q[k] = *reinterpret_cast<const uchar4*>(p);
-                        lb[k] = v > 0 ? p[-1] : q[k].x;             // ends of the superset: those outputs are unused
-                        rb[k] = v < NVEC - 1 ? p[4] : q[k].w;
+                    for (int k = 0; k < NIT; k++) {
+                        const int i = tid + 256 * k;
+                        if (i < RAWH * NVEC) {
+                            const int j = i / NVEC, v = i - j * NVEC;
+                            const unsigned char* p = pe_smem + staged_off + j * PE_STAGE_PITCH + 4 * v;
+                            q[k] = *reinterpret_cast<const uchar4*>(p);
+                            lb[k] = v > 0 ? p[-1] : q[k].x;
+                            rb[k] = v < NVEC - 1 ? p[4] : q[k].w;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NIT; k++) {      // all loads of the thread in flight before the first use
+                        const int i = tid + 256 * k;
+                        if (i < RAWH * NVEC) {
+                            const int j = i / NVEC, v = i - j * NVEC;
+                            const int fy = yin ? uby + j : reflect101(uby + j, H);
+                            const unsigned char* p = srcb + (size_t)fy * a.src_pitch + (x0 - 8) + 4 * v;
+                            q[k] = *reinterpret_cast<const uchar4*>(p);
+                            lb[k] = v > 0 ? p[-1] : q[k].x;         // ends of the superset: those outputs are unused
+                            rb[k] = v < NVEC - 1 ? p[4] : q[k].w;
+                        }
                     }
                 }
 #pragma unroll
@@ -392,7 +411,7 @@ k_polyexp2(PolyArgs a)
     const int xb = warp * 2 + (lane >> 4);              // 0..15
     const int lx0 = xb * 4;
     const int gy = y0 + ly, gx0 = x0 + lx0;
-    if (gy >= H || gx0 >= W) return;
+    if (gy >= H || gx0 >= W) return;                    // (the caller's barriers come after every thread is back)
     // channel order of the outputs: o0 = d/dy (b3), o1 = d/dx (b2), o2 = yy (b1,b5), o3 = xx (b1,b4), o4 = xy (b6).
     // One source array at a time, results reduced to f32 as soon as they are complete, to keep the register peak low.
     float o0[4], o1[4], o2[4], o3[4], o4[4];
@@ -455,8 +474,144 @@ k_polyexp2(PolyArgs a)
 }
 
 template <int N, int SRC>
+__global__ void __launch_bounds__(256, 4)
+k_polyexp2(PolyArgs a)
+{
+    extern __shared__ __align__(128) unsigned char pe_smem[];
+    pe_tile<N, SRC>(a, pe_smem, blockIdx.x * 64, blockIdx.y * 16, blockIdx.z, -1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_polyexp2_tma<N>: the scale-0 kernel as a PERSISTENT grid (4 CTAs per SM) with TMA halo tiles.  A CTA walks
+// tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; while it computes tile t, the raw u8 patch of its next tile
+// (RAWH rows x 96 bytes: the 64 columns plus a 16-byte halo either side -- TMA wants a 16-byte aligned start) is fetched by ONE
+// cp.async.bulk.tensor.3d into the other of two shared-memory buffers and signalled on an mbarrier, so the global
+// load latency of the staging pass is hidden behind the previous tile's vertical and horizontal passes.
+// Tiles whose patch crosses the frame border (TMA fills zeros, the pre-blur needs reflect-101) read global memory
+// through the per-element path of pe_tile instead.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pe_mbar_wait(unsigned mbar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <int N> struct PeTma {
+    static constexpr int TW = 64, TH = 16, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1), RAWH = PH + 2, HBP = TW + 16;
+    static constexpr int PATCH = RAWH * PE_STAGE_PITCH;                           // bytes of one staged patch (box 96 x RAWH)
+    static constexpr int PATCH_AL = (PATCH + 127) & ~127;
+    static constexpr int BASE = (3 * TH * RP * 8 + RAWH * HBP * 4 + 127) & ~127;  // pe_tile's arrays (aligned-frame paths only)
+    static constexpr int SMEM = BASE + 2 * PATCH_AL + 16;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256, 4)
+k_polyexp2_tma(const __grid_constant__ CUtensorMap tmap, PolyArgs a, int tiles_x, int tiles_y, int ntiles)
+{
+    using G = PeTma<N>;
+    extern __shared__ __align__(128) unsigned char pe_smem[];
+    unsigned char* const raw_base = pe_smem + G::BASE;                           // two patches, G::PATCH_AL apart
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(pe_smem + G::BASE + 2 * G::PATCH_AL);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto tile_of = [&](int t, int& x0, int& y0, int& z) {
+        const int bx = t % tiles_x, r = t / tiles_x;
+        x0 = bx * G::TW; y0 = (r % tiles_y) * G::TH; z = r / tiles_y;
+    };
+    auto stageable = [&](int x0, int y0) {
+        return x0 >= 8 && x0 + G::TW + 8 <= a.W && y0 - N - 1 >= 0 && y0 - N - 1 + G::RAWH <= a.H;
+    };
+    auto issue = [&](int t, int buf) {                                           // one thread
+        int x0, y0, z;
+        tile_of(t, x0, y0, z);
+        if (!stageable(x0, y0)) return;
+        const unsigned mb = mbar0 + 8u * buf, dst = (unsigned)__cvta_generic_to_shared(raw_base + buf * G::PATCH_AL);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(G::PATCH) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(dst), "l"(&tmap), "r"(x0 - 16), "r"(y0 - N - 1), "r"(z), "r"(mb) : "memory");
+    };
+    unsigned phase = 0u;                                                         // bit b = parity to wait for on buffer b
+    int t = blockIdx.x;
+    if (tid == 0 && t < ntiles) issue(t, 0);
+    for (int it = 0; t < ntiles; t += gridDim.x, it++) {
+        const int buf = it & 1;
+        // the other buffer was last read in the staging pass of the previous tile, which ended before that tile's barriers
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, buf ^ 1);
+        int x0, y0, z;
+        tile_of(t, x0, y0, z);
+        int staged_off = -1;
+        if (stageable(x0, y0)) {
+            pe_mbar_wait(mbar0 + 8u * buf, (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+            staged_off = G::BASE + buf * G::PATCH_AL + 8;                        // column x0-8 of the box that starts at x0-16
+        }
+        pe_tile<N, 1>(a, pe_smem, x0, y0, z, staged_off);
+        // No barrier here: the next tile's staging pass only writes sHB (last read before this tile's second barrier),
+        // and its first barrier comes before anything overwrites sR, which this tile's horizontal pass is still reading.
+    }
+}
+
+// Engine option "polyexp_tma" (default 0).  Measured on B200 (tools/ab.sh, 1080p, 24 frames per launch): 9.6 ms per
+// 300-pair step against 8.4 ms for the one-tile-per-CTA kernel -- the staging latency it hides (~15 % of the kernel) is
+// smaller than what the persistent loop adds (tile decode, barrier wait, spills around the f64 pass), so it is kept
+// as a tested alternative (tests/test_gpu_parity.py::test_polyexp_tma_path_is_bit_identical), not as the default.
+static int g_polyexp_tma = 0;
+void set_polyexp_tma(int v) { g_polyexp_tma = v; }
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Persistent TMA variant of the scale-0 launch; returns false (nothing launched) when the frames do not meet TMA's
+// alignment rules or the driver entry point is missing, and the caller falls back to k_polyexp2<N, 1>.
+template <int N>
+static bool run_polyexp2_tma(Launch& L, const PolyArgs& a, int batch)
+{
+    using G = PeTma<N>;
+    if (!g_polyexp_tma || (a.W & 15) || (a.src_pitch & 15) || (a.src_item & 15) || ((uintptr_t)a.src & 15) || a.W < 16) return false;
+    static PFN_tensorMapEncodeTiled encode = nullptr;
+    static int sms = 0;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = (PFN_tensorMapEncodeTiled)fn;
+        else
+            cudaGetLastError();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_polyexp2_tma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    }
+    if (!encode || sms <= 0) return false;
+    CUtensorMap tm;
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)a.src_pitch, (cuuint64_t)(batch > 1 ? a.src_item : a.src_pitch * a.H)};
+    const cuuint32_t box[3] = {(cuuint32_t)PE_STAGE_PITCH, (cuuint32_t)G::RAWH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(a.src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    const int tx = divup(a.W, G::TW), ty = divup(a.H, G::TH), ntiles = tx * ty * batch;
+    const int grid = std::min(ntiles, sms * 4);
+    L.run("polyexp_scale0", [&](cudaStream_t s) { k_polyexp2_tma<N><<<grid, 256, G::SMEM, s>>>(tm, a, tx, ty, ntiles); });
+    return true;
+}
+
+template <int N, int SRC>
 static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
 {
+    if (SRC == 1 && run_polyexp2_tma<N>(L, a, batch)) return;
     constexpr int TW = 64, TH = 16, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1);
     size_t smem = sizeof(double) * 3 * TH * RP +
                   sizeof(float) * (SRC == 0 ? (size_t)0 : (size_t)(PH + 2) * (PW + 2) + (size_t)(PH + 2) * PW);

@@ -585,3 +585,18 @@ def test_shot_bgr_equals_host_preprocessing_then_shot(eng, oracle):
         assert np.array_equal(a["magsum"], b["magsum"])
         c = eng.pairs_bgr(frames[:-1], frames[1:], dsize=dsize, want_magsum=True)
         assert np.array_equal(c["magsum"], b["magsum"])
+
+
+def test_polyexp_tma_path_is_bit_identical(eng):
+    """Engine option "polyexp_tma": the persistent scale-0 kernel with TMA-staged halo tiles gives the same bits as the
+    default kernel (same arithmetic; only where the raw patch comes from differs), on a frame with interior and border tiles."""
+    f = _textured(448, 200, 5)[0]
+    frames = np.stack([np.roll(f, (i, 2 * i), (0, 1)) for i in range(4)])
+    ref = eng.shot(frames, want_bgr=True, want_flow=True)
+    eng.set_option("polyexp_tma", 1)
+    try:
+        got = eng.shot(frames, want_bgr=True, want_flow=True)
+    finally:
+        eng.set_option("polyexp_tma", 0)
+    assert np.array_equal(got["flow"], ref["flow"])
+    assert np.array_equal(got["bgr"], ref["bgr"])
