@@ -163,6 +163,8 @@ int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, in
  *   "batch"            pairs per launch inside a shot (0 = chosen from the frame size)
  *   "batch_scale0"     pairs per launch at scale 0 (0 = same as batch)
  *   "iter_prefetch"    1 (default) = software L2 prefetch in the iteration kernel
+ *   "hsv_table"        1 (default) = the picture kernel looks HSV->BGR up in a 65536-entry table built by the same
+ *                      arithmetic at ofb_create; 0 = evaluates the conversion per pixel (identical output)
  *   "polyexp_tma"      1 = scale-0 polynomial expansion as a persistent grid whose halo tiles are staged by TMA
  *                      (cp.async.bulk.tensor + mbarrier, double-buffered); bit-identical results, measured slower
  *                      than the default one-tile-per-CTA kernel on B200, so off by default */

@@ -190,14 +190,16 @@ void launch_resize_u8(Launch& L, const uint8_t* src, size_t src_item, size_t src
 
 // viz.cu -- Appendix B
 // batched over pairs: flow / bgr / minmax / sums advance by *_item per batch element
+// table: 65536-entry (H byte << 8 | V byte) -> B | G<<8 | R<<16 lookup built by launch_build_hsv_table, or nullptr (arithmetic)
+void launch_build_hsv_table(Launch& L, unsigned* table);
 void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax /* 2 per item */,
-                          uint8_t* bgr, size_t bgr_item, int batch, bool minmax_done = false);
+                          uint8_t* bgr, size_t bgr_item, int batch, bool minmax_done = false, const unsigned* table = nullptr);
 void launch_minmax_reset_batch(Launch& L, unsigned* minmax, int batch);
 void launch_sum_magnitude_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, double* acc /* 1 per item */,
                                 float* out /* 1 per item */, int batch);
 void launch_minmax_mag(Launch& L, const float2* flow, size_t n, unsigned* minmax /* [2], pre-set */);
 void launch_minmax_reset(Launch& L, unsigned* minmax);
-void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned* minmax, uint8_t* bgr);
+void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned* minmax, uint8_t* bgr, const unsigned* table = nullptr);
 void launch_cart_to_polar(Launch& L, const float2* flow, size_t n, float* mag, float* ang);
 void launch_sum_magnitude(Launch& L, const float2* flow, size_t n, double* acc /* pre-zeroed */, float* out);
 

@@ -97,6 +97,8 @@ struct ofb_context {
     unsigned* minmax = nullptr;         // 2 per batch item
     double* sumacc = nullptr;           // 1 per batch item
     float* sumout = nullptr;            // device staging of magnitude sums (batch items)
+    unsigned* hsv_table = nullptr;      // (H byte << 8 | V byte) -> packed BGR, built once (viz.cu)
+    bool use_hsv_table = true;          // option "hsv_table"
     float* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
     // 8-bit bilinear resize tables of the last (source, destination) geometry (preprocess.cu)
@@ -508,7 +510,8 @@ int upload_frame(ofb_context* ctx, const void* src, size_t pitch, int W, int H, 
 void picture(ofb_context* ctx, Launch& L, const float2* d_flow, size_t flow_item, size_t n, uint8_t* d_bgr, size_t bgr_item, int count,
              bool minmax_done = false)
 {
-    launch_picture_batch(L, d_flow, flow_item, n, ctx->minmax, d_bgr, bgr_item, count, minmax_done);
+    launch_picture_batch(L, d_flow, flow_item, n, ctx->minmax, d_bgr, bgr_item, count, minmax_done,
+                         ctx->use_hsv_table ? ctx->hsv_table : nullptr);
 }
 
 // Pairs per launch inside a shot: enough pixels per launch to fill 148 SMs at the coarse scales and to
@@ -647,10 +650,20 @@ int ofb_create(int device, ofb_context** out)
     ok(cudaMalloc((void**)&c->minmax, sizeof(unsigned) * 2 * MAX_BATCH + 256));
     ok(cudaMalloc((void**)&c->sumacc, sizeof(double) * MAX_BATCH + 256));
     ok(cudaMalloc((void**)&c->sumout, sizeof(float) * MAX_BATCH + 256));
+    ok(cudaMalloc((void**)&c->hsv_table, sizeof(unsigned) * 65536));
     if (rc != cudaSuccess) {
         std::string m = std::string("context setup: ") + cudaGetErrorString(rc);
         delete c;
         return fail(nullptr, OFB_ERR_CUDA, m);
+    }
+    {
+        Launch L{c->s_compute, &c->prof};
+        launch_build_hsv_table(L, c->hsv_table);
+        if (cudaStreamSynchronize(c->s_compute) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            delete c;
+            return fail(nullptr, OFB_ERR_CUDA, "context setup: building the HSV->BGR table failed");
+        }
+        c->prof.reset();
     }
     *out = c;
     return OFB_OK;
@@ -665,7 +678,7 @@ void ofb_destroy(ofb_context* ctx)
     free_plan(ctx->plan);
     for (int i = 0; i < 6; i++) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     if (ctx->rs_tab) cudaFree(ctx->rs_tab);
-    cudaFree(ctx->minmax); cudaFree(ctx->sumacc); cudaFree(ctx->sumout);
+    cudaFree(ctx->minmax); cudaFree(ctx->sumacc); cudaFree(ctx->sumout); cudaFree(ctx->hsv_table);
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_frame_free[i]);
         cudaEventDestroy(ctx->ev_out_ready[i]); cudaEventDestroy(ctx->ev_out_free[i]);
@@ -1327,6 +1340,7 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!strcmp(name, "iter_ilp")) { set_iter_ilp(value); return OFB_OK; }
     if (!strcmp(name, "iter_prefetch")) { set_iter_prefetch(value); return OFB_OK; }
     if (!strcmp(name, "polyexp_tma")) { set_polyexp_tma(value); return OFB_OK; }
+    if (!strcmp(name, "hsv_table")) { ctx->use_hsv_table = value != 0; return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "profile")) {

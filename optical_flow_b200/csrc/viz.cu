@@ -94,15 +94,20 @@ __device__ __forceinline__ NormCoef norm_coef(const unsigned* mm)
     return c;
 }
 
-__device__ __forceinline__ uchar3 pixel_bgr(float2 f, NormCoef nc)
+// f32 flow -> the two bytes NumPy stores into hsv[...,0] and hsv[...,2] (visualize_optical_flow.py:53-54)
+__device__ __forceinline__ void quantise_hv(float2 f, NormCoef nc, int& hq, int& vq)
 {
     Polar p = polar_of(f.x, f.y);
     float ang = deg_to_rad_cv(p.ang_deg);
     float hue = (ang * 180.f) / (float)3.14159265358979323846;   // NumPy: f32 * 180 then / f32(pi)
-    int hq = ((int)hue) & 255;
+    hq = ((int)hue) & 255;
     float nv = fmaf(p.mag, nc.fs, nc.fsh);
-    int vq = ((int)nv) & 255;
-    // cv::cvtColor(COLOR_HSV2BGR), 8-bit, S = 255, vector-body rounding (truncate)
+    vq = ((int)nv) & 255;
+}
+
+// cv::cvtColor(COLOR_HSV2BGR), 8-bit, S = 255, vector-body rounding (truncate): (H byte, V byte) -> B | G<<8 | R<<16
+__device__ __forceinline__ unsigned hsv_s255_to_bgr(int hq, int vq)
+{
     float h = (float)hq * (6.f / 180.f);
     const float s = 255.f * (1.f / 255.f);
     float v = (float)vq * (1.f / 255.f);
@@ -121,28 +126,42 @@ __device__ __forceinline__ uchar3 pixel_bgr(float2 f, NormCoef nc)
         default: b = t2; g = t1; r = t0; break;
     }
     int bi = (int)(b * 255.f), gi = (int)(g * 255.f), ri = (int)(r * 255.f);
-    uchar3 o;
-    o.x = (unsigned char)min(max(bi, 0), 255);
-    o.y = (unsigned char)min(max(gi, 0), 255);
-    o.z = (unsigned char)min(max(ri, 0), 255);
-    return o;
+    return (unsigned)min(max(bi, 0), 255) | ((unsigned)min(max(gi, 0), 255) << 8) | ((unsigned)min(max(ri, 0), 255) << 16);
+}
+
+// The colour conversion has a 16-bit domain, so the batched picture kernel looks it up instead of spending ~8 of its
+// ~11 XU-pipe operations per pixel (I2F / F2I / floor) on it: table[h << 8 | v] is filled once per context by the SAME
+// function, so table and arithmetic agree by construction (and both are pinned by tests/golden/hsv2bgr_table.npz).
+__global__ void k_build_hsv_table(unsigned* __restrict__ table) { table[blockIdx.x * 256 + threadIdx.x] = hsv_s255_to_bgr(blockIdx.x, threadIdx.x); }
+
+void launch_build_hsv_table(Launch& L, unsigned* table)
+{
+    L.run("hsv_table", [&](cudaStream_t s) { k_build_hsv_table<<<256, 256, 0, s>>>(table); });
+}
+
+template <bool LUT>
+__device__ __forceinline__ unsigned pixel_bgr(float2 f, NormCoef nc, const unsigned* __restrict__ table)
+{
+    int hq, vq;
+    quantise_hv(f, nc, hq, vq);
+    return LUT ? __ldg(table + ((hq << 8) | vq)) : hsv_s255_to_bgr(hq, vq);
 }
 
 // 4 pixels per thread: two 16-byte flow loads, three 4-byte picture stores.
+template <bool LUT>
 __global__ void __launch_bounds__(256)
 k_flow_to_bgr_v4(const float4* __restrict__ flow4, size_t n4, const unsigned* __restrict__ mm, uint32_t* __restrict__ bgr,
-                 size_t flow_item4 = 0, size_t bgr_item4 = 0)
+                 const unsigned* __restrict__ table, size_t flow_item4 = 0, size_t bgr_item4 = 0)
 {
     flow4 += (size_t)blockIdx.y * flow_item4; bgr += (size_t)blockIdx.y * bgr_item4; mm += 2 * blockIdx.y;
     NormCoef nc = norm_coef(mm);
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
         float4 a = flow4[2 * g], b = flow4[2 * g + 1];
-        uchar3 p0 = pixel_bgr(make_float2(a.x, a.y), nc), p1 = pixel_bgr(make_float2(a.z, a.w), nc);
-        uchar3 p2 = pixel_bgr(make_float2(b.x, b.y), nc), p3 = pixel_bgr(make_float2(b.z, b.w), nc);
-        uint32_t w0 = p0.x | (p0.y << 8) | (p0.z << 16) | ((uint32_t)p1.x << 24);
-        uint32_t w1 = p1.y | (p1.z << 8) | (p2.x << 16) | ((uint32_t)p2.y << 24);
-        uint32_t w2 = p2.z | (p3.x << 8) | (p3.y << 16) | ((uint32_t)p3.z << 24);
-        bgr[3 * g] = w0; bgr[3 * g + 1] = w1; bgr[3 * g + 2] = w2;
+        const unsigned p0 = pixel_bgr<LUT>(make_float2(a.x, a.y), nc, table), p1 = pixel_bgr<LUT>(make_float2(a.z, a.w), nc, table);
+        const unsigned p2 = pixel_bgr<LUT>(make_float2(b.x, b.y), nc, table), p3 = pixel_bgr<LUT>(make_float2(b.z, b.w), nc, table);
+        bgr[3 * g] = p0 | (p1 << 24);
+        bgr[3 * g + 1] = (p1 >> 8) | (p2 << 16);
+        bgr[3 * g + 2] = (p2 >> 16) | (p3 << 8);
     }
 }
 
@@ -153,8 +172,8 @@ k_flow_to_bgr_scalar(const float2* __restrict__ flow, size_t n, const unsigned* 
     flow += (size_t)blockIdx.y * flow_item; bgr += (size_t)blockIdx.y * bgr_item; mm += 2 * blockIdx.y;
     NormCoef nc = norm_coef(mm);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        uchar3 p = pixel_bgr(flow[i], nc);
-        bgr[3 * i] = p.x; bgr[3 * i + 1] = p.y; bgr[3 * i + 2] = p.z;
+        const unsigned p = pixel_bgr<false>(flow[i], nc, nullptr);
+        bgr[3 * i] = (uint8_t)p; bgr[3 * i + 1] = (uint8_t)(p >> 8); bgr[3 * i + 2] = (uint8_t)(p >> 16);
     }
 }
 
@@ -223,13 +242,14 @@ void launch_minmax_mag(Launch& L, const float2* flow, size_t n, unsigned* minmax
     L.run("minmax_mag", [&](cudaStream_t s) { k_minmax_mag<<<reduce_grid(n, 8), 256, 0, s>>>(flow, n, minmax); });
 }
 
-void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned* minmax, uint8_t* bgr)
+void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned* minmax, uint8_t* bgr, const unsigned* table)
 {
     bool vec = (n % 4 == 0) && ((uintptr_t)flow % 16 == 0) && ((uintptr_t)bgr % 4 == 0);
     if (vec) {
         size_t n4 = n / 4;
         L.run("flow_to_bgr_v4", [&](cudaStream_t s) {
-            k_flow_to_bgr_v4<<<reduce_grid(n4, 2), 256, 0, s>>>((const float4*)flow, n4, minmax, (uint32_t*)bgr);
+            if (table) k_flow_to_bgr_v4<true><<<reduce_grid(n4, 2), 256, 0, s>>>((const float4*)flow, n4, minmax, (uint32_t*)bgr, table);
+            else k_flow_to_bgr_v4<false><<<reduce_grid(n4, 2), 256, 0, s>>>((const float4*)flow, n4, minmax, (uint32_t*)bgr, nullptr);
         });
     } else {
         L.run("flow_to_bgr_scalar", [&](cudaStream_t s) {
@@ -244,7 +264,7 @@ void launch_minmax_reset_batch(Launch& L, unsigned* minmax, int batch)
 }
 
 void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_t n, unsigned* minmax,
-                          uint8_t* bgr, size_t bgr_item, int batch, bool minmax_done)
+                          uint8_t* bgr, size_t bgr_item, int batch, bool minmax_done, const unsigned* table)
 {
     if (!minmax_done) {
         launch_minmax_reset_batch(L, minmax, batch);
@@ -256,7 +276,8 @@ void launch_picture_batch(Launch& L, const float2* flow, size_t flow_item, size_
         size_t n4 = n / 4;
         dim3 g2(reduce_grid(n4, 2), batch);
         L.run("flow_to_bgr_v4", [&](cudaStream_t s) {
-            k_flow_to_bgr_v4<<<g2, 256, 0, s>>>((const float4*)flow, n4, minmax, (uint32_t*)bgr, flow_item / 2, bgr_item / 4);
+            if (table) k_flow_to_bgr_v4<true><<<g2, 256, 0, s>>>((const float4*)flow, n4, minmax, (uint32_t*)bgr, table, flow_item / 2, bgr_item / 4);
+            else k_flow_to_bgr_v4<false><<<g2, 256, 0, s>>>((const float4*)flow, n4, minmax, (uint32_t*)bgr, nullptr, flow_item / 2, bgr_item / 4);
         });
     } else {
         dim3 g2(reduce_grid(n, 4), batch);
