@@ -619,3 +619,36 @@ def test_hsv_table_and_arithmetic_pictures_are_identical(eng, oracle):
         eng.set_option("hsv_table", 1)
     assert np.array_equal(a, b)
     assert np.array_equal(a, oracle.viz(flow, 0))
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (68, 52), (72, 33), (132, 76), (260, 140), (324, 200), (448, 17)])
+def test_aligned_width_geometries_shot_equals_pairs_and_oracle(eng, oracle, W, H):
+    """Widths that are multiples of 4 take the vectorised staging paths (polyexp, column-first pyramid) with every
+    mix of interior / border tiles; the batched shot must equal per-pair calls bit for bit and the oracle within tolerance."""
+    f0, f1 = _smooth_pair(W, H, 7 * W + H)
+    f2 = np.ascontiguousarray(np.flipud(f0))
+    frames = np.stack([f0, f1, f2, f1])
+    res = eng.shot(frames, want_bgr=True, want_flow=True)
+    kw = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    for t in range(3):
+        one = eng.calc(frames[t], frames[t + 1], None, **kw)
+        assert np.array_equal(res["flow"][t], one), (W, H, t)
+    ref = oracle.farneback(f0, f1, None, **kw)
+    mean, mx = epe(res["flow"][0], ref)
+    assert mean <= EPE_MEAN_TOL and mx <= EPE_MAX_TOL, (W, H, mean, mx)
+
+
+@pytest.mark.parametrize("sw,sh,dsize", [(131, 77, None), (131, 77, (64, 38)), (200, 113, (129, 72)), (66, 50, None)])
+def test_shot_bgr_with_unaligned_frames(eng, oracle, sw, sh, dsize):
+    """Decoded frames whose byte size is not a multiple of 4 (scalar gray kernel, unaligned staging offsets inside a chunk)."""
+    rng = np.random.default_rng(sw + sh)
+    frames = rng.integers(0, 256, (7, sh, sw, 3), dtype=np.uint8)
+    gray = np.stack([oracle.bgr2gray(f if dsize is None else oracle.resize_u8(f, dsize)) for f in frames])
+    eng.set_option("batch", 3)                          # several chunks, frames at odd offsets inside the staging buffer
+    try:
+        a = eng.shot_bgr(frames, dsize=dsize, want_bgr=True, want_magsum=True, want_gray=True)
+        b = eng.shot(gray, want_bgr=True, want_magsum=True)
+    finally:
+        eng.set_option("batch", 0)
+    assert np.array_equal(a["gray"], gray)
+    assert np.array_equal(a["bgr"], b["bgr"]) and np.array_equal(a["magsum"], b["magsum"])
