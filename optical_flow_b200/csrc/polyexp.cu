@@ -184,6 +184,15 @@ void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const Po
 // keeps the 16 rows of a half-warp on distinct bank pairs, and each thread re-uses its 4+2N-wide
 // register window for 4 outputs.
 // ------------------------------------------------------------------------------------------------
+// Tile geometry of k_polyexp2 / k_polyexp2_tma: 64 columns x PE_TH rows, one thread per 4 outputs of the horizontal pass.
+#ifndef OFB_PE_TH
+#define OFB_PE_TH 16
+#endif
+constexpr int PE_TW = 64, PE_TH = OFB_PE_TH, PE_THREADS = PE_TH * 16, PE_MINB = 1024 / PE_THREADS;
+static_assert(PE_TH == 8 || PE_TH == 16 || PE_TH == 32, "tile height");
+// vertical pass: row groups per column (VG), rows a group holds inputs for (VR), row stride between groups (VS)
+constexpr int PE_VG = PE_TH == 16 ? 3 : PE_TH == 32 ? 4 : 1, PE_VR = PE_TH == 16 ? 6 : 8, PE_VS = PE_TH == 16 ? 5 : 8;
+
 // One 64 x 16 tile of frame z.  `staged_off` (SRC 1 only): byte offset inside pe_smem of the tile's raw u8 patch -- rows
 // y0-N-1 .. y0+TH+N, columns from x0-8 on, PE_STAGE_PITCH bytes per row -- when TMA has already put it in shared
 // memory (k_polyexp2_tma), or -1: the patch is read from global memory.  All barriers are block-uniform.
@@ -192,7 +201,7 @@ template <int N, int SRC>
 __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_smem, const int x0, const int y0, const int z,
                                         const int staged_off)
 {
-    constexpr int TW = 64, TH = 16;
+    constexpr int TW = PE_TW, TH = PE_TH;
     constexpr int PW = TW + 2 * N, PH = TH + 2 * N;
     constexpr int RP = (PW | 1);                       // odd pitch (in doubles) of the vertical-pass results
     constexpr int RAWW = PW + 2, RAWH = PH + 2;
@@ -211,12 +220,12 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
     // straight into registers -- from global memory (SRC 0) or from the row-blurred patch (SRC 1, interior tiles), in
     // which case the column pass of the pre-blur is applied on the fly -- so the level image never sits in shared
     // memory and two block-wide passes (and their barriers) disappear.  Same arithmetic, same order as the tiled form.
-    constexpr int VG = 3, VR = 6, VS = 5;               // groups, rows per group, row stride between groups
-    static_assert(VS * (VG - 1) + VR == TH && VG * PW <= 256, "vertical pass: thread = (column, row group)");
+    constexpr int VG = PE_VG, VR = PE_VR, VS = PE_VS;    // groups, rows per group, row stride between groups
+    static_assert(VS * (VG - 1) + VR == TH && VG * PW <= PE_THREADS, "vertical pass: thread = (column, row group)");
     auto vertical_from = [&](const float (&b)[VR + 2 * N], int g, int px) {
 #pragma unroll
         for (int o = 0; o < VR; o++) {
-            if (o == 0 && g > 0) continue;                   // row 5g belongs to group g-1
+            if (VR > VS && o == 0 && g > 0) continue;        // overlapping groups: row VS*g belongs to group g-1
             const int cidx = o + N;
             float r0 = b[cidx] * a.g[0], r1 = 0.f, r2 = 0.f;
 #pragma unroll
@@ -262,14 +271,14 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
             // row pass of the pre-blur while loading: 4 outputs per aligned 4-pixel load (+ the two neighbour bytes)
             constexpr int NVEC = (TW + 16) / 4;
             constexpr int HBP = TW + 16;                 // sHB column = column offset inside the superset
-            constexpr int NIT = (RAWH * NVEC + 255) / 256;
+            constexpr int NIT = (RAWH * NVEC + PE_THREADS - 1) / PE_THREADS;
             float* sHBf = sI;
             if (xin) {
                 uchar4 q[NIT]; unsigned char lb[NIT], rb[NIT];
                 if (staged_off >= 0 && yin) {            // shared-memory loads (the compiler sees the address space)
 #pragma unroll
                     for (int k = 0; k < NIT; k++) {
-                        const int i = tid + 256 * k;
+                        const int i = tid + PE_THREADS * k;
                         if (i < RAWH * NVEC) {
                             const int j = i / NVEC, v = i - j * NVEC;
                             const unsigned char* p = pe_smem + staged_off + j * PE_STAGE_PITCH + 4 * v;
@@ -281,7 +290,7 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
                 } else {
 #pragma unroll
                     for (int k = 0; k < NIT; k++) {      // all loads of the thread in flight before the first use
-                        const int i = tid + 256 * k;
+                        const int i = tid + PE_THREADS * k;
                         if (i < RAWH * NVEC) {
                             const int j = i / NVEC, v = i - j * NVEC;
                             const int fy = yin ? uby + j : reflect101(uby + j, H);
@@ -294,7 +303,7 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
                 }
 #pragma unroll
                 for (int k = 0; k < NIT; k++) {
-                    const int i = tid + 256 * k;
+                    const int i = tid + PE_THREADS * k;
                     if (i < RAWH * NVEC) {
                         const int j = i / NVEC, v = i - j * NVEC;
                         const float fl = u8_to_f32(lb[k]), f0 = u8_to_f32(q[k].x), f1 = u8_to_f32(q[k].y), f2 = u8_to_f32(q[k].z),
@@ -308,7 +317,7 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
                     }
                 }
             } else {
-                for (int i = tid; i < RAWH * HBP; i += 256) {
+                for (int i = tid; i < RAWH * HBP; i += PE_THREADS) {
                     const int j = i / HBP, cc = i - j * HBP;
                     const int c = x0 - 8 + cc;
                     if (c >= 0 && c < W) {
@@ -352,7 +361,7 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
             }
             vertical_done = true;
         } else {
-            for (int i = tid; i < RAWH * RAWW; i += 256) {
+            for (int i = tid; i < RAWH * RAWW; i += PE_THREADS) {
                 int j = i / RAWW, ii = i - j * RAWW;
                 int fy = reflect101(uby + j, H), fx = reflect101(ubx + ii, W);
                 const unsigned char* row = srcb + (size_t)fy * a.src_pitch;
@@ -360,7 +369,7 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
             }
             __syncthreads();
             // row pass at the (replicate-clamped) patch columns
-            for (int i = tid; i < RAWH * PW; i += 256) {
+            for (int i = tid; i < RAWH * PW; i += PE_THREADS) {
                 int j = i / PW, px = i - j * PW;
                 int cx = min(max(x0 - N + px, 0), W - 1) - ubx;            // raw column of the centre tap
                 const float* r = raw + j * RAWW + cx;
@@ -371,7 +380,7 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
             }
             __syncthreads();
             // column pass at the (replicate-clamped) patch rows; overwrites the raw patch
-            for (int i = tid; i < PH * PW; i += 256) {
+            for (int i = tid; i < PH * PW; i += PE_THREADS) {
                 int py = i / PW, px = i - py * PW;
                 int cy = min(max(y0 - N + py, 0), H - 1) - uby;
                 const float* c = sHB + cy * PW + px;
@@ -386,7 +395,7 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
 
     // ---- vertical pass, tiled form (border tiles of the fused scale-0 path): f32 in cv2's order, widened once ----
     if (!vertical_done) {
-        for (int i = tid; i < TH * PW; i += 256) {
+        for (int i = tid; i < TH * PW; i += PE_THREADS) {
             int ty = i / PW, px = i - ty * PW;
             const float* col = sI + (ty + N) * PW + px;
             float r0 = col[0] * a.g[0], r1 = 0.f, r2 = 0.f;
@@ -407,8 +416,9 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
 
     // ---- horizontal pass (f64) ----
     const int lane = tid & 31, warp = tid >> 5;
-    const int ly = lane & 15;
-    const int xb = warp * 2 + (lane >> 4);              // 0..15
+    // 8 warps cover 16 rows x 16 four-pixel blocks (PE_TH = 8: 4 warps cover 8 rows x 16 blocks)
+    const int ly = PE_TH == 8 ? (lane & 7) : (lane & 15) + 16 * (warp >> 3);
+    const int xb = PE_TH == 8 ? warp * 4 + (lane >> 3) : (warp & 7) * 2 + (lane >> 4);        // 0..15
     const int lx0 = xb * 4;
     const int gy = y0 + ly, gx0 = x0 + lx0;
     if (gy >= H || gx0 >= W) return;                    // (the caller's barriers come after every thread is back)
@@ -474,11 +484,11 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
 }
 
 template <int N, int SRC>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(PE_THREADS, PE_MINB)
 k_polyexp2(PolyArgs a)
 {
     extern __shared__ __align__(128) unsigned char pe_smem[];
-    pe_tile<N, SRC>(a, pe_smem, blockIdx.x * 64, blockIdx.y * 16, blockIdx.z, -1);
+    pe_tile<N, SRC>(a, pe_smem, blockIdx.x * PE_TW, blockIdx.y * PE_TH, blockIdx.z, -1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,7 +510,7 @@ __device__ __forceinline__ void pe_mbar_wait(unsigned mbar, unsigned parity)
 }
 
 template <int N> struct PeTma {
-    static constexpr int TW = 64, TH = 16, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1), RAWH = PH + 2, HBP = TW + 16;
+    static constexpr int TW = PE_TW, TH = PE_TH, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1), RAWH = PH + 2, HBP = TW + 16;
     static constexpr int PATCH = RAWH * PE_STAGE_PITCH;                           // bytes of one staged patch (box 96 x RAWH)
     static constexpr int PATCH_AL = (PATCH + 127) & ~127;
     static constexpr int BASE = (3 * TH * RP * 8 + RAWH * HBP * 4 + 127) & ~127;  // pe_tile's arrays (aligned-frame paths only)
@@ -508,7 +518,7 @@ template <int N> struct PeTma {
 };
 
 template <int N>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(PE_THREADS, PE_MINB)
 k_polyexp2_tma(const __grid_constant__ CUtensorMap tmap, PolyArgs a, int tiles_x, int tiles_y, int ntiles)
 {
     using G = PeTma<N>;
@@ -603,8 +613,8 @@ static bool run_polyexp2_tma(Launch& L, const PolyArgs& a, int batch)
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
     const int tx = divup(a.W, G::TW), ty = divup(a.H, G::TH), ntiles = tx * ty * batch;
-    const int grid = std::min(ntiles, sms * 4);
-    L.run("polyexp_scale0", [&](cudaStream_t s) { k_polyexp2_tma<N><<<grid, 256, G::SMEM, s>>>(tm, a, tx, ty, ntiles); });
+    const int grid = std::min(ntiles, sms * PE_MINB);
+    L.run("polyexp_scale0", [&](cudaStream_t s) { k_polyexp2_tma<N><<<grid, PE_THREADS, G::SMEM, s>>>(tm, a, tx, ty, ntiles); });
     return true;
 }
 
@@ -612,7 +622,7 @@ template <int N, int SRC>
 static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
 {
     if (SRC == 1 && run_polyexp2_tma<N>(L, a, batch)) return;
-    constexpr int TW = 64, TH = 16, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1);
+    constexpr int TW = PE_TW, TH = PE_TH, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1);
     size_t smem = sizeof(double) * 3 * TH * RP +
                   sizeof(float) * (SRC == 0 ? (size_t)0 : (size_t)(PH + 2) * (PW + 2) + (size_t)(PH + 2) * PW);
     static bool attr_set = false;
@@ -622,7 +632,7 @@ static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
     }
     dim3 grid(divup(a.W, TW), divup(a.H, TH), batch);
     const char* nm = SRC == 0 ? "polyexp_level" : "polyexp_scale0";
-    L.run(nm, [&](cudaStream_t s) { k_polyexp2<N, SRC><<<grid, 256, smem, s>>>(a); });
+    L.run(nm, [&](cudaStream_t s) { k_polyexp2<N, SRC><<<grid, PE_THREADS, smem, s>>>(a); });
 }
 
 bool polyexp2_supported(int n) { return n == 3 || n == 5 || n == 7; }
