@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "1080p Farneback frame-pairs/sec"
 UNIT = "pairs/s"
-TRAFFIC_JSON = "r1g_traffic.json"      # measured DRAM bytes per pair and kernel (tools/ncu_traffic.py) of the current kernels
+TRAFFIC_JSON = "r1i_traffic.json"      # measured DRAM bytes per pair and kernel (tools/ncu_traffic.py) of the current kernels
 PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
 
 # algorithmic HBM bytes per pixel of a launch, per kernel (SURVEY.md 8d stage model)

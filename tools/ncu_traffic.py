@@ -18,7 +18,7 @@ FAMILY = [(r"k_polyexp2<\d+, [12]>", "polyexp_scale0"), (r"k_polyexp2<", "polyex
           (r"k_iter<\d+, 1, \d+, 0>", "iter_fused"), (r"k_iter<\d+, 0, \d+, 0>", "iter_last"),
           (r"k_iter<\d+, 1, \d+, 1>", "iter_fused_gauss"), (r"k_iter<\d+, 0, \d+, 1>", "iter_last_gauss"),
           (r"k_flow_to_bgr", "flow_to_bgr_v4"), (r"k_minmax_reset", "minmax_reset"), (r"k_minmax", "minmax_mag"),
-          (r"k_bgr2gray", "bgr2gray"), (r"k_resize_u8", "resize_u8")]
+          (r"k_bgr2gray", "bgr2gray"), (r"k_resize_u8", "resize_u8"), (r"k_build_hsv_table", "hsv_table")]
 
 
 def unit_scale(u):
