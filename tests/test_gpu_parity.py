@@ -652,3 +652,27 @@ def test_shot_bgr_with_unaligned_frames(eng, oracle, sw, sh, dsize):
         eng.set_option("batch", 0)
     assert np.array_equal(a["gray"], gray)
     assert np.array_equal(a["bgr"], b["bgr"]) and np.array_equal(a["magsum"], b["magsum"])
+
+
+@pytest.mark.parametrize("kind", ["zeros", "white", "stripes_x", "stripes_y", "checker", "step_at_tile_edge"])
+def test_degenerate_frames_through_the_shot_path(eng, oracle, kind):
+    """Flat, saturated and hard-edged frames (edges placed on the 64-column / 16-row tile boundaries of the staging
+    kernels): finite output, flat frames give exactly zero flow, everything else stays within the parity tolerance of
+    the oracle away from cv2's own chaotic in/out-of-bounds switch (A.8) -- compared on the 3-scale median."""
+    W, H = 256, 96
+    ys, xs = np.mgrid[0:H, 0:W]
+    base = {"zeros": np.zeros((H, W)), "white": np.full((H, W), 255), "stripes_x": ((xs // 8) % 2) * 255,
+            "stripes_y": ((ys // 8) % 2) * 255, "checker": (((xs // 16) + (ys // 16)) % 2) * 200 + 20,
+            "step_at_tile_edge": np.where(xs < 128, 30, 220) + np.where(ys < 48, 0, 25)}[kind].astype(np.uint8)
+    nxt = np.roll(base, (1, 2), (0, 1))
+    frames = np.stack([base, nxt, base])
+    res = eng.shot(frames, want_bgr=True, want_flow=True, want_magsum=True)
+    assert np.isfinite(res["flow"]).all() and np.isfinite(res["magsum"]).all()
+    if kind in ("zeros", "white"):
+        assert not res["flow"].any() and not res["bgr"].any()
+        return
+    kw = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+    ref = oracle.farneback(base, nxt, None, **kw)
+    d = np.sqrt(((res["flow"][0].astype(np.float64) - ref) ** 2).sum(-1))
+    assert np.median(d) <= 1e-4 and d.mean() <= 2e-2, (kind, float(np.median(d)), float(d.mean()), float(d.max()))
+    assert np.array_equal(res["bgr"][0], oracle.viz(res["flow"][0], 0))
