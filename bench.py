@@ -3,19 +3,30 @@
 
     python bench.py --gpus N --steps K --warmup W            # this engine (CUDA, through the C-ABI)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (cv2) on host cores
+    python bench.py --workload feature|long_video|sharded_shot ...   # the other BASELINE configs (one JSON line each)
 
 A "step" is one pass of the hot path over one shot: 300 consecutive 1920x1080 frame pairs with the
 reference's parameters (optical_flow.py:53-59) plus the HSV picture of every pair
 (visualize_optical_flow.py:48-55).  With N > 1 (torchrun, one process per GPU) every rank processes its own
 300-pair shot -- pairs are independent, there is no collective on the data path ("scaling": "weak").
 
-Legs of the default run (one JSON line on rank 0):
-  value      device-resident: the 301 u8 frames already in HBM, pictures written to HBM; CUDA events.
-  e2e        the same shot through ofb_shot_host: frames in pinned host memory, H2D of every frame and D2H
-             of every picture inside the timed region (CUDA events from first upload to last download).
-  roofline   per-kernel CUDA-event durations (option "profile") of one extra pass; the dominant kernel's
-             algorithmic bytes per launch / its average duration, against MEASURED_PEAKS.json.
-  cpu_baseline  cv2.calcOpticalFlowFarneback + the four picture lines on this box's host cores (bounded sample).
+The default line (workload "shot"), rank 0:
+  value            THE PROTOCOL NUMBER (SURVEY.md 8d / BASELINE.md 4.6): frames start in pinned HOST memory; the H2D copy of
+                   every u8 frame and the D2H copy of every u8 BGR picture are INSIDE the timed region (CUDA events from the
+                   first upload to the last download on the engine's own streams, max over ranks), through ofb_shot_host.
+  e2e              the same K calls timed by the HOST wall clock around the public Python call (ctypes, submission and the
+                   final synchronisation included).
+  device_resident  frames already in HBM, pictures left in HBM (ofb_shot_device): what the kernels alone sustain.
+  legs             the same shot with other deliveries of the result: "jpeg" (the reference's artefact,
+                   visualize_optical_flow.py:57-58: the picture leaves the GPU as a baseline JPEG byte stream) and "feature"
+                   (optical_flow.py:61-64: one float per pair); "rough_motion": the raw-picture protocol on 10-20 px
+                   piecewise-constant motion instead of the smooth 2.5 px affine.
+  parity           after the timing: pairs at every kind of schedule seam compared with cv2 itself.
+  roofline         per-kernel CUDA-event durations (option "profile") of one extra pass; the dominant kernel's
+                   algorithmic bytes per launch / its average duration, against MEASURED_PEAKS.json.
+  latency          one drop-in calcOpticalFlowFarneback call with pageable NumPy arrays (flow D2H included), and one cv2
+                   call in one process with cv2's default threads.
+  cpu_baseline     cv2.calcOpticalFlowFarneback + the four picture lines on this box's host cores (bounded sample).
 """
 import argparse
 import json
@@ -32,7 +43,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "1080p Farneback frame-pairs/sec"
 UNIT = "pairs/s"
-TRAFFIC_JSON = "r1i_traffic.json"      # measured DRAM bytes per pair and kernel (tools/ncu_traffic.py) of the current kernels
+TRAFFIC_JSON = "r2_traffic.json"       # measured DRAM bytes per pair and kernel (tools/ncu_traffic.py) of the current kernels
 PARAMS = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
 
 # algorithmic HBM bytes per pixel of a launch, per kernel (SURVEY.md 8d stage model)
@@ -215,14 +226,8 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------------------
 # this engine
 # --------------------------------------------------------------------------------------------------
-def run_ours(args, rank, local_rank, world):
+def make_engine(args, local_rank):
     import optical_flow_b200 as ofb
-    from optical_flow_b200 import dist
-    import synth_frames
-
-    W, H, P = args.width, args.height, args.pairs
-    n = W * H
-    numa_cpus = dist.bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     eng = ofb.Farneback(local_rank)          # raises if the CUDA library / device is missing: no fallback
     if args.batch > 0:
         eng.set_option("batch", args.batch)
@@ -237,58 +242,193 @@ def run_ours(args, rank, local_rank, world):
         tsync = torch.cuda.synchronize
     except Exception:
         tsync = eng.synchronize
+    return eng, tsync
+
+
+def parity_check(eng, frames, W, H, P):
+    """After the timing, outside it: the benchmarked entry points (default batch) against cv2 itself at the pairs where
+    the schedule has a seam (chunk starts 0 | B/4 | 3B/4 | ..., the wrap of the 2B-slot frame ring, the tail chunks)."""
+    try:
+        import cv2
+        from oracle import cv2_reference
+    except Exception as e:     # cv2 missing on this box: say so, do not invent a number
+        return {"checked": False, "why": "cv2 not importable: %r" % (e,)}
+    n = W * H
+    B = 24 if (W, H) == (1920, 1080) else 0
+    pairs = sorted({t for t in (0, B // 4 - 1, B // 4, 3 * B // 4 - 1, 3 * B // 4, 2 * B - 1, 2 * B, P // 2,
+                                P - B // 4 - 1, P - B // 4, P - 1) if 0 <= t < P})
+    d_frames = eng.device_alloc(frames.nbytes)
+    d_bgr = eng.device_alloc(P * n * 3)
+    d_flow = eng.device_alloc(P * n * 8)
+    try:
+        eng.h2d(d_frames, frames)
+        eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, d_flow=d_flow, **PARAMS)
+        host_bgr = eng.shot(frames, want_bgr=True, **PARAMS)["bgr"]
+        worst_mean = worst_max = 0.0
+        worst_w1 = 1.0
+        same = True
+        fl = np.empty((H, W, 2), np.float32)
+        pic = np.empty((H, W, 3), np.uint8)
+        for t in pairs:
+            eng.d2h(fl, d_flow + t * n * 8)
+            eng.d2h(pic, d_bgr + t * n * 3)
+            same = same and bool(np.array_equal(pic, host_bgr[t]))
+            cf = cv2_reference.farneback(frames[t], frames[t + 1], None, **PARAMS)
+            cb = cv2_reference.viz(cf)
+            d = np.sqrt(((fl.astype(np.float64) - cf) ** 2).sum(-1))
+            worst_mean = max(worst_mean, float(d.mean())); worst_max = max(worst_max, float(d.max()))
+            worst_w1 = min(worst_w1, float((np.abs(pic.astype(np.int16) - cb.astype(np.int16)) <= 1).all(-1).mean()))
+    finally:
+        for p in (d_frames, d_bgr, d_flow):
+            eng.device_free(p)
+    ok = worst_mean <= 1e-3 and worst_max <= 1e-2 and worst_w1 >= 0.999 and same
+    return {"checked": True, "against": "cv2 " + cv2.__version__, "entry_points": ["ofb_shot_device", "ofb_shot_host"],
+            "pairs": pairs, "epe_mean_px": worst_mean, "epe_max_px": worst_max, "picture_within_1": worst_w1,
+            "host_equals_device_bitwise": same, "tolerance": "mean <= 1e-3 px, max <= 1e-2 px, picture +-1 on >= 99.9 %",
+            "ok": ok}
+
+
+def latency_leg(eng, frames, W, H):
+    """one drop-in call as the reference makes it (optical_flow.py:51-59): pageable NumPy frames in,
+    pageable float32 flow out (the 8*W*H-byte D2H included); and the same call on cv2 in one process, default threads."""
+    import optical_flow_b200 as ofb
+    prev, nxt = np.array(frames[0]), np.array(frames[1])       # pageable copies
+    kw = PARAMS
+    ts = []
+    for i in range(24):
+        t0 = time.perf_counter()
+        ofb_flow = eng.calc(prev, nxt, None, kw["pyr_scale"], kw["levels"], kw["winsize"], kw["iterations"], kw["poly_n"],
+                            kw["poly_sigma"], kw["flags"])
+        ts.append(1e3 * (time.perf_counter() - t0))
+    out = {"dropin_latency_ms": float(np.median(ts[4:])), "dropin_calls": len(ts) - 4,
+           "dropin_what": "optical_flow_b200.calcOpticalFlowFarneback(prev, next, None, ...) %dx%d, pageable arrays, "
+                          "H2D of both frames + kernels + D2H of the f32 flow, median" % (W, H)}
+    reuse = np.empty_like(ofb_flow)
+    ts = []
+    for i in range(24):
+        t0 = time.perf_counter()
+        eng.calc(prev, nxt, reuse, kw["pyr_scale"], kw["levels"], kw["winsize"], kw["iterations"], kw["poly_n"],
+                 kw["poly_sigma"], kw["flags"])
+        ts.append(1e3 * (time.perf_counter() - t0))
+    out["dropin_latency_inplace_flow_ms"] = float(np.median(ts[4:]))
+    try:
+        import cv2
+        ts = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            cv2.calcOpticalFlowFarneback(prev, nxt, None, kw["pyr_scale"], kw["levels"], kw["winsize"], kw["iterations"],
+                                         kw["poly_n"], kw["poly_sigma"], kw["flags"])
+            ts.append(1e3 * (time.perf_counter() - t0))
+        out["cpu_latency_ms"] = float(np.median(ts[1:]))
+        out["cpu_what"] = "cv2 %s, one process, cv2.getNumThreads() = %d" % (cv2.__version__, cv2.getNumThreads())
+    except Exception as e:
+        out["cpu_latency_ms"] = None
+        out["cpu_what"] = "cv2 not importable: %r" % (e,)
+    return out
+
+
+def run_shot(args, rank, local_rank, world):
+    import optical_flow_b200 as ofb
+    from optical_flow_b200 import dist
+    import synth_frames
+
+    W, H, P = args.width, args.height, args.pairs
+    n = W * H
+    numa_cpus = dist.bind_to_gpu_numa_node(local_rank) if world > 1 else 0
+    eng, tsync = make_engine(args, local_rank)
 
     # synthetic shot (seeded per rank), generated straight into pinned host memory
     frames = ofb.pinned_empty((P + 1, H, W), np.uint8)
-    synth_frames.shot(W, H, P + 1, seed=100 + rank, out=frames)
+    if args.motion == "rough":
+        synth_frames.shot_rough(W, H, P + 1, seed=100 + rank, out=frames)
+    else:
+        synth_frames.shot(W, H, P + 1, seed=100 + rank, out=frames)
     bgr_host = ofb.pinned_empty((P, H, W, 3), np.uint8)
-
-    d_frames = eng.device_alloc(frames.nbytes)
-    d_bgr = eng.device_alloc(P * n * 3)
-    eng.h2d(d_frames, frames)
 
     def barrier_sync():
         eng.synchronize(); tsync(); dist.barrier()
 
-    # ---- leg 1: device-resident ("value") ----
+    def timed_host_leg(call, steps, warm):
+        """K calls of a host-API leg: (max-over-ranks CUDA-event ms, max-over-ranks wall seconds)."""
+        for _ in range(warm):
+            call()
+        eng.reset_kernel_stats()
+        barrier_sync()
+        w0 = time.perf_counter()
+        ms = 0.0
+        for _ in range(steps):
+            ms += call()["device_ms"]
+        barrier_sync()
+        w1 = time.perf_counter()
+        return dist.reduce_max(ms), dist.reduce_max(w1 - w0), w0, w1
+
+    total_pairs = dist.reduce_sum(P * args.steps)
+
+    # ---- leg 1: the protocol number ("value") and the wall-clock number of the same calls ("e2e") ----
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_ev, t_wall, w0, w1 = timed_host_leg(lambda: eng.shot(frames, want_bgr=True, out_bgr=bgr_host, **PARAMS),
+                                          args.steps, args.warmup)
+    clocks = sampler.stop(w0, w1)
+    launches = int(sum(v[0] for v in eng.kernel_stats().values()))      # kernels launched inside the timed region
+    value = total_pairs / (t_ev / 1e3)
+    e2e_value = total_pairs / t_wall
+    probe = np.array(bgr_host[P - 1])
+    assert probe.max() > 0 and probe.std() > 0, "the host leg produced an empty picture"
+
+    # ---- leg 2: device-resident (kernels only) ----
+    d_frames = eng.device_alloc(frames.nbytes)
+    d_bgr = eng.device_alloc(P * n * 3)
+    eng.h2d(d_frames, frames)
     for _ in range(args.warmup):
         eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
-    eng.reset_kernel_stats()
     barrier_sync()
-    wall0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
         dev_ms += eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
     barrier_sync()
-    wall1 = time.perf_counter()
-    wall = wall1 - wall0
-    clocks = sampler.stop(wall0, wall1)
-    launches = sum(v[0] for v in eng.kernel_stats().values())
     t_dev = dist.reduce_max(dev_ms)
-    t_wall = dist.reduce_max(wall)
-    total_pairs = dist.reduce_sum(P * args.steps)
-    value = total_pairs / (t_dev / 1e3)
+    dev_value = total_pairs / (t_dev / 1e3)
+    chk = np.empty((H, W, 3), np.uint8)
+    eng.d2h(chk, d_bgr + (P - 1) * n * 3)
+    assert np.array_equal(chk, probe), "host-API picture differs from the device-resident one"
 
-    # sanity: the pictures of the last step are real (non-constant) results
-    probe = np.empty((H, W, 3), np.uint8)
-    eng.d2h(probe, d_bgr + (P - 1) * n * 3)
-    assert probe.max() > 0 and probe.std() > 0, "device leg produced an empty picture"
+    # ---- leg 3: other deliveries of the same shot ----
+    legs = {}
+    steps2 = max(3, args.steps // 2)
+    t_ev_f, t_wall_f, _, _ = timed_host_leg(lambda: eng.shot(frames, want_bgr=False, want_magsum=True, **PARAMS), steps2, 2)
+    pf = dist.reduce_sum(P * steps2)
+    legs["feature"] = {"value": pf / (t_ev_f / 1e3), "wall_value": pf / t_wall_f, "unit": UNIT,
+                       "what": "optical_flow.py:61-64 delivery: np.sum(mag) per pair (4 B/pair D2H), frames H2D inside",
+                       "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": 4 * P}
+    if hasattr(eng, "shot_jpeg"):
+        jres = {}
+        def jcall():
+            r = eng.shot_jpeg(frames, **PARAMS)
+            jres["bytes"] = int(r["sizes"].sum())
+            return r
+        t_ev_j, t_wall_j, _, _ = timed_host_leg(jcall, steps2, 2)
+        legs["jpeg"] = {"value": pf / (t_ev_j / 1e3), "wall_value": pf / t_wall_j, "unit": UNIT,
+                        "what": "visualize_optical_flow.py:57-58 delivery: the picture leaves the GPU as the baseline-JPEG "
+                                "byte stream cv2.imwrite would produce (quality 95, 4:2:0), frames H2D inside",
+                        "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": jres.get("bytes")}
+    if args.motion == "smooth" and not args.no_rough:
+        synth_frames.shot_rough(W, H, P + 1, seed=100 + rank, out=frames)
+        t_ev_r, t_wall_r, _, _ = timed_host_leg(lambda: eng.shot(frames, want_bgr=True, out_bgr=bgr_host, **PARAMS), steps2, 2)
+        eng.h2d(d_frames, frames)
+        eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
+        barrier_sync()
+        rms = 0.0
+        for _ in range(steps2):
+            rms += eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
+        barrier_sync()
+        legs["rough_motion"] = {"value": pf / (t_ev_r / 1e3), "device_resident": pf / (dist.reduce_max(rms) / 1e3), "unit": UNIT,
+                                "what": "the raw-picture protocol on synth_frames.shot_rough: 10-20 px per pair, piecewise "
+                                        "constant in 6x4 blocks, random directions (the gathers' worst case)"}
+        synth_frames.shot(W, H, P + 1, seed=100 + rank, out=frames)      # back to the benchmark shot
+        eng.h2d(d_frames, frames)
 
-    # ---- leg 2: end to end through the host API ("e2e") ----
-    for _ in range(max(1, min(args.warmup, 2))):
-        eng.shot(frames, want_bgr=True, out_bgr=bgr_host, **PARAMS)
-    barrier_sync()
-    e2e_ms = 0.0
-    for _ in range(args.steps):
-        e2e_ms += eng.shot(frames, want_bgr=True, out_bgr=bgr_host, **PARAMS)["device_ms"]
-    barrier_sync()
-    t_e2e = dist.reduce_max(e2e_ms)
-    e2e_value = total_pairs / (t_e2e / 1e3)
-    assert np.array_equal(bgr_host[P - 1], probe), "host-API picture differs from the device-resident one"
-
-    # ---- leg 3: per-kernel CUDA-event durations (one extra pass, not part of the timed regions) ----
+    # ---- leg 4: per-kernel CUDA-event durations (one extra pass, not part of the timed regions) ----
     roof = None
     kernels = {}
     if rank == 0:
@@ -315,6 +455,7 @@ def run_ours(args, rank, local_rank, world):
                 frames_factor = (P + 1) if name.startswith("polyexp") else P
                 byts = KERNEL_BYTES_PER_PX[name] * px_per_launch_total[name] * frames_factor
                 k["achieved_gbs"] = round(byts / (ms * 1e-3) / 1e9, 1)
+                k["frac_of_peak"] = round(byts / (ms * 1e-3) / 1e9 / peak, 4)
                 k["alg_bytes_per_launch"] = round(byts / cnt, 1)
             kernels[name] = k
         dom = max((kv for kv in kernels.items() if "achieved_gbs" in kv[1]), key=lambda kv: kv[1]["total_ms"], default=None)
@@ -334,43 +475,224 @@ def run_ours(args, rank, local_rank, world):
                     "avg_launch_ms": round(dom[1]["total_ms"] / dom[1]["launches"], 5),
                     "share_of_step": dom[1]["share"], "peak_source": peak_src,
                     "how": "CUDA events around every launch of one extra %d-pair pass (option profile)" % P}
+    eng.device_free(d_frames)
+    eng.device_free(d_bgr)
 
-    # ---- leg 4: the reference's CPU path beside it (rank 0, N = 1 only) ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        ntasks = max(2 * cores, 16) if W * H <= 1920 * 1080 else max(cores, 4)
-        r, kind, ver, dt = cpu_reference_rate(np.array(frames[:9]), ntasks, cores)
-        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": "%d pairs of the same %dx%d shot in %.1f s, %d processes x cv2.setNumThreads(1); %s; %s"
-                         % (ntasks, W, H, dt, cores, ver, cpu_model())}
+    # ---- leg 5 (rank 0): parity of the benchmarked entry points against cv2, latencies, the CPU baseline ----
+    parity = lat = cpu = None
+    if rank == 0:
+        if not args.no_parity:
+            parity = parity_check(eng, frames, W, H, P)
+        if world == 1 and not args.no_latency:
+            lat = latency_leg(eng, frames, W, H)
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            ntasks = max(8 * cores, 64) if W * H <= 1920 * 1080 else max(2 * cores, 8)
+            r, kind, ver, dt = cpu_reference_rate(np.array(frames[:9]), ntasks, cores)
+            cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "%d pairs of the same %dx%d shot in %.1f s, %d processes x cv2.setNumThreads(1); %s; %s"
+                             % (ntasks, W, H, dt, cores, ver, cpu_model())}
 
     if rank == 0:
         peak, peak_src = peaks()
-        alg = ofb.algorithmic_bytes(W, H, with_viz=True, **PARAMS)
-        per_gpu = value / world
+        alg_pair = ofb.algorithmic_bytes(W, H, with_viz=True, **PARAMS)
+        # a shot expands every frame ONCE, an independent pair twice: B_pair charges 2 x (N u8 read + I write + I read + R write)
+        # per scale; inside a shot half of that is shared with the neighbouring pair (SURVEY.md 8d allows B_pair; both are stated)
+        sched = ofb.scale_schedule(W, H, PARAMS["pyr_scale"], PARAMS["levels"])
+        per_frame = sum(n + 28.0 * w * h for (_, w, h, _, _) in sched)
+        alg_shot = alg_pair - per_frame * (P - 1.0) / P
+        per_gpu_dev = dev_value / world
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": t_dev / args.steps, "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": t_ev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_text(W, H, P), "pairs_per_step_per_gpu": P,
+                           "motion": ("smooth affine, ~2.5 px per pair" if args.motion == "smooth"
+                                      else "rough: 10-20 px per pair, piecewise constant"),
+                           "timed_region": "H2D of every u8 frame from pinned host memory + all kernels + D2H of every u8 BGR "
+                                           "picture to pinned host memory; CUDA events first upload -> last download",
                            "l2": "inputs larger than L2: every step streams %d MB of frames and %d MB of pictures "
                                  "plus ~300 MB of per-pair intermediates through a 126 MB L2"
                                  % (frames.nbytes // 2**20, bgr_host.nbytes // 2**20),
                            "sharding": "one %d-pair shot per GPU, no collective" % P,
                            "host_affinity": ("rank bound to %d CPUs near its GPU (NVML)" % numa_cpus) if numa_cpus else "default"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
-                        "d2h_bytes_per_step": int(bgr_host.nbytes), "ms_per_step": t_e2e / args.steps},
-                "gpu_launches": int(launches),
+                        "d2h_bytes_per_step": int(bgr_host.nbytes), "ms_per_step": 1e3 * t_wall / args.steps,
+                        "clock": "host wall clock around the public Python call (eng.shot), barrier + synchronize on both sides"},
+                "device_resident": {"value": dev_value, "unit": UNIT, "ms_per_step": t_dev / args.steps,
+                                    "what": "ofb_shot_device: frames already in HBM, pictures left in HBM (kernels only)"},
+                "legs": legs,
+                "gpu_launches": launches,
                 "clocks": clocks,
                 "roofline": roof,
-                "roofline_pipeline": {"alg_bytes_per_pair": alg, "achieved": per_gpu * alg / 1e9, "peak": peak,
-                                      "unit": "GB/s", "frac": per_gpu * alg / 1e9 / peak, "peak_source": peak_src},
+                "roofline_pipeline": {"what": "device-resident pairs/s x algorithmic bytes per pair, per GPU",
+                                      "alg_bytes_per_pair": alg_pair, "achieved": per_gpu_dev * alg_pair / 1e9,
+                                      "frac": per_gpu_dev * alg_pair / 1e9 / peak,
+                                      "alg_bytes_per_pair_shot_adjusted": alg_shot,
+                                      "achieved_shot_adjusted": per_gpu_dev * alg_shot / 1e9,
+                                      "frac_shot_adjusted": per_gpu_dev * alg_shot / 1e9 / peak,
+                                      "frac_protocol_value": (value / world) * alg_pair / 1e9 / peak,
+                                      "peak": peak, "unit": "GB/s", "peak_source": peak_src},
                 "kernels": kernels,
-                "cpu_baseline": cpu,
-                "wall_s": t_wall}
+                "parity": parity,
+                "latency": lat,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
-    eng.device_free(d_frames)
-    eng.device_free(d_bgr)
+    dist.barrier()
+
+
+# --------------------------------------------------------------------------------------------------
+# other BASELINE configs as their own workloads (one JSON line each; kept under profiles/)
+# --------------------------------------------------------------------------------------------------
+def run_feature(args, rank, local_rank, world):
+    """optical_flow.py's regime (--frame_width 129): independent pairs of small frames, one float per pair
+    (optical_flow.py:83-99 with calculate_optical_flow :49-66), through ofb_pairs_host."""
+    import optical_flow_b200 as ofb
+    from optical_flow_b200 import dist
+    import synth_frames
+    W, H, P = args.width, args.height, args.pairs
+    eng, tsync = make_engine(args, local_rank)
+    bank = synth_frames.shot(W, H, 65, seed=300 + rank)
+    idx = np.arange(P) % 64
+    prev = ofb.pinned_empty((P, H, W), np.uint8); prev[:] = bank[idx]
+    nxt = ofb.pinned_empty((P, H, W), np.uint8); nxt[:] = bank[idx + 1]
+
+    def sync():
+        eng.synchronize(); tsync(); dist.barrier()
+    for _ in range(args.warmup):
+        eng.pairs(prev, nxt, want_magsum=True, **PARAMS)
+    eng.reset_kernel_stats()
+    sync()
+    w0 = time.perf_counter()
+    ms = 0.0
+    for _ in range(args.steps):
+        r = eng.pairs(prev, nxt, want_magsum=True, **PARAMS)
+        ms += r["device_ms"]
+    sync()
+    wall = time.perf_counter() - w0
+    launches = sum(v[0] for v in eng.kernel_stats().values())
+    t_ev, t_wall = dist.reduce_max(ms), dist.reduce_max(wall)
+    total = dist.reduce_sum(P * args.steps)
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg = ofb.algorithmic_bytes(W, H, with_viz=False, **PARAMS) + 8.0 * W * H
+        v = total / (t_ev / 1e3)
+        print(json.dumps({"metric": "%dx%d Farneback feature pairs/sec (summed magnitude per pair)" % (W, H), "value": v, "unit": UNIT,
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ev / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "feature path: %d independent %dx%d pairs per step per GPU, reference parameters, "
+                                                 "np.sum(mag) per pair; H2D of both frames of every pair and D2H of the sums inside "
+                                                 "the timed region (ofb_pairs_host)" % (P, W, H)},
+                          "e2e": {"value": total / t_wall, "unit": UNIT, "h2d_bytes_per_step": int(prev.nbytes + nxt.nbytes),
+                                  "d2h_bytes_per_step": 4 * P, "clock": "host wall clock"},
+                          "gpu_launches": int(launches),
+                          "roofline_pipeline": {"alg_bytes_per_pair": alg, "achieved": v / world * alg / 1e9, "peak": peak,
+                                                "frac": v / world * alg / 1e9 / peak, "unit": "GB/s", "peak_source": peak_src},
+                          "magsum_first": float(r["magsum"][0])}), flush=True)
+    dist.barrier()
+
+
+def run_long_video(args, rank, local_rank, world):
+    """configs[3]: a long 1080p video of `--pairs` (default 20 000) frame pairs in shots of 50-400 pairs (seeded), whole shots
+    assigned to ranks longest-first (shard_shots).  Frames come from a per-rank bank of 65 distinct PINNED frames (the stand-in
+    for a decoder's output buffers) and are handed to the engine as a pointer table (ofb_shot_host_v): nothing is assembled
+    on the host, so wall clock and device events agree."""
+    import optical_flow_b200 as ofb
+    from optical_flow_b200 import dist
+    import synth_frames
+    W, H = args.width, args.height
+    total_pairs = args.pairs if args.pairs != 300 else 20000
+    if world > 1:
+        dist.bind_to_gpu_numa_node(local_rank)
+    rng = np.random.default_rng(7)
+    lengths = []
+    while sum(lengths) < total_pairs:
+        lengths.append(int(min(rng.integers(50, 401), total_pairs - sum(lengths))))
+    mine = ofb.shard_shots(lengths, world)[rank]
+    eng, tsync = make_engine(args, local_rank)
+    bank_n = 65
+    bank = ofb.pinned_empty((bank_n, H, W), np.uint8)
+    synth_frames.shot(W, H, bank_n, seed=1000 + rank, out=bank)
+    bank_frames = [bank[i] for i in range(bank_n)]
+    max_len = max((n for _, _, n in mine), default=1)
+    out = ofb.pinned_empty((max_len, H, W, 3), np.uint8)
+
+    def frame_list(shot, first, n):      # forward-backward walk through the bank: consecutive frames differ by one warp step
+        idx = (np.arange(first, first + n + 1) + shot * 7) % (2 * bank_n - 2)
+        idx = np.where(idx < bank_n, idx, 2 * bank_n - 2 - idx)
+        return [bank_frames[i] for i in idx]
+
+    eng.shot_frames(frame_list(0, 0, 48), want_bgr=True, out_bgr=out, **PARAMS)       # warm-up: workspaces, clocks
+    eng.synchronize(); tsync(); dist.barrier()
+    t0 = time.perf_counter()
+    dev_ms, done, checksum = 0.0, 0, 0
+    for (shot, first, n) in mine:
+        r = eng.shot_frames(frame_list(shot, first, n), want_bgr=True, out_bgr=out, **PARAMS)
+        dev_ms += r["device_ms"]
+        done += n
+        checksum = (checksum * 31 + int(out[n - 1, H // 2, W // 2].sum())) % 1000003
+    eng.synchronize()
+    wall = time.perf_counter() - t0
+    dist.barrier()
+    t_dev, t_wall, total = dist.reduce_max(dev_ms), dist.reduce_max(wall), dist.reduce_sum(done)
+    sums = dist.gather_ints([checksum])
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": total / t_wall, "unit": UNIT, "n_gpus": world, "higher_is_better": True,
+                          "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "configs[3]: %d pairs of %dx%d in %d shots of 50-400 pairs, whole shots sharded "
+                                                 "longest-first over %d GPU(s); raw BGR picture per pair D2H; frames uploaded from "
+                                                 "65 pinned decoder-style buffers per rank via ofb_shot_host_v"
+                                                 % (int(total), W, H, len(lengths), world)},
+                          "pairs": int(total), "value_clock": "host wall clock of the slowest rank, all shots",
+                          "pairs_per_s_device_events": total / (t_dev / 1e3), "wall_s": t_wall,
+                          "shots_on_rank0": len(mine), "checksums": [s[0] for s in sums]}), flush=True)
+    dist.barrier()
+
+
+def run_sharded_shot(args, rank, local_rank, world):
+    """north_star: "a shot's pairs are sharded across the 8 GPUs": ONE 300-pair shot, rank r takes shard_pairs(P, world, r)
+    plus one overlap frame (strong scaling; the seam frames are expanded twice).  Pictures are checked bit for bit against
+    an unsharded run of the same shot on rank 0."""
+    import optical_flow_b200 as ofb
+    from optical_flow_b200 import dist
+    import synth_frames
+    import hashlib
+    W, H, P = args.width, args.height, args.pairs
+    if world > 1:
+        dist.bind_to_gpu_numa_node(local_rank)
+    eng, tsync = make_engine(args, local_rank)
+    s, e = ofb.shard_pairs(P, world, rank)
+    allf = synth_frames.shot(W, H, P + 1, seed=100)                  # every rank generates the same shot, keeps its range
+    frames = ofb.pinned_empty((e - s + 1, H, W), np.uint8)
+    frames[:] = allf[s:e + 1]
+    out = ofb.pinned_empty((e - s, H, W, 3), np.uint8)
+
+    def sync():
+        eng.synchronize(); tsync(); dist.barrier()
+    for _ in range(args.warmup):
+        eng.shot(frames, want_bgr=True, out_bgr=out, **PARAMS)
+    sync()
+    w0 = time.perf_counter()
+    ms = 0.0
+    for _ in range(args.steps):
+        ms += eng.shot(frames, want_bgr=True, out_bgr=out, **PARAMS)["device_ms"]
+    sync()
+    wall = time.perf_counter() - w0
+    t_ev, t_wall = dist.reduce_max(ms), dist.reduce_max(wall)
+    digest = int(hashlib.sha1(out.tobytes()).hexdigest()[:15], 16)
+    digests = dist.gather_ints([digest])
+    if rank == 0:
+        same = None
+        if world > 1 and not args.no_parity:        # the unsharded shot on rank 0: shard r must reproduce its slice bit for bit
+            whole = eng.shot(allf, want_bgr=True, **PARAMS)["bgr"]
+            same = all(int(hashlib.sha1(whole[a:b].tobytes()).hexdigest()[:15], 16) == digests[r][0]
+                       for r in range(world) for (a, b) in [ofb.shard_pairs(P, world, r)])
+        print(json.dumps({"metric": METRIC, "value": P * args.steps / (t_ev / 1e3), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ev / args.steps, "higher_is_better": True,
+                          "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "ONE %d-pair %dx%d shot split into %d contiguous pair ranges (+1 overlap frame each), "
+                                                 "H2D frames + D2H raw pictures inside the timed region" % (P, W, H, world)},
+                          "e2e": {"value": P * args.steps / t_wall, "unit": UNIT, "clock": "host wall clock"},
+                          "shards_equal_unsharded_bitwise": same}), flush=True)
     dist.barrier()
 
 
@@ -380,11 +702,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="shot", choices=["shot", "feature", "long_video", "sharded_shot"])
+    ap.add_argument("--motion", default="smooth", choices=["smooth", "rough"])
     ap.add_argument("--pairs", type=int, default=300)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--ref-pairs-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-rough", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (experiments)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per launch inside a shot (0 = engine default)")
     ap.add_argument("--batch-scale0", type=int, default=-1, help="pairs per launch at scale 0 (-1 = default, 0 = same as --batch)")
@@ -397,7 +724,13 @@ def main():
         return
     if world > 1:
         dist.init("nccl")
-    run_ours(args, rank, local_rank, world)
+    if args.workload == "feature":
+        if (args.width, args.height) == (1920, 1080):
+            args.width, args.height = 129, 72
+        if args.pairs == 300:
+            args.pairs = 4096
+    {"shot": run_shot, "feature": run_feature, "long_video": run_long_video,
+     "sharded_shot": run_sharded_shot}[args.workload](args, rank, local_rank, world)
     dist.finalize()
 
 

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define OFB_ABI_VERSION 2
+#define OFB_ABI_VERSION 3
 
 /* flags of cv2.calcOpticalFlowFarneback */
 #define OFB_OPTFLOW_USE_INITIAL_FLOW 4
@@ -119,6 +119,10 @@ int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtyp
                   const ofb_params* p, uint8_t* bgr, float* magsum, float* flow);
 int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p,
                   uint8_t* bgr, float* magsum, float* flow, float* device_ms);
+/* ofb_shot_host with the frames at n_frames separate addresses (a decoder's own buffers, pinned or pageable): frame i is
+ * frames[i], W*H bytes.  Nothing is assembled on the host; every frame is uploaded straight from where it lies. */
+int ofb_shot_host_v(ofb_context* ctx, const uint8_t* const* frames, int n_frames, int W, int H, const ofb_params* p,
+                    uint8_t* bgr, float* magsum, float* flow, float* device_ms);
 /* n_pairs INDEPENDENT pairs (prev[i], next[i]), each (H, W) uint8 tightly packed: the window loop of
  * optical_flow.py:83-99, whose pairs need not share frames.  Same outputs as ofb_shot_host. */
 int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, int n_pairs, int W, int H,

@@ -78,6 +78,7 @@ def load():
     proto("ofb_sum_magnitude_device", i, vp, vp, i, i, vp)
     proto("ofb_pair_host", i, vp, vp, vp, i, i, i, pp, vp, vp, vp)
     proto("ofb_shot_host", i, vp, vp, i, i, i, pp, vp, vp, vp, fp)
+    proto("ofb_shot_host_v", i, vp, C.POINTER(vp), i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_shot_device", i, vp, vp, i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_pairs_host", i, vp, vp, vp, i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_bgr_to_gray_host", i, vp, vp, i, i, vp)

@@ -152,7 +152,6 @@ void launch_polyexp(Launch& L, const float* I, int W, int H, int pitch, const Po
 // batched, unrolled variant: src_kind 0 = level image (f32), 1 = u8 frame + fused [1/4 1/2 1/4]^2 pre-blur
 // (scale 0), 2 = f32 frame + the same pre-blur.  Returns false when poly_n has no unrolled instance.
 bool polyexp2_supported(int n);
-void set_polyexp_tma(int v);            // 1 = scale-0 polyexp as a persistent grid with TMA-staged halo tiles
 void launch_polyexp2(Launch& L, int src_kind, const PolyArgs& a, int batch);
 
 // matrices.cu -- A.2 and A.8
@@ -168,9 +167,7 @@ void launch_deinterleave5(Launch& L, const float* src /* (H,W,5) */, int W, int 
 // iter.cu -- A.8 / A.9 / A.11 batched
 void launch_um0(Launch& L, int src, const Um0Args& a, int batch);
 bool iter_supported(int winsize);
-void set_iter_ilp(int v);
-void set_iter_prefetch(int v);
-void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count);
+void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch);
 
 // blur_solve.cu -- A.9 / A.10
 void launch_blur_solve_box(Launch& L, Planes5 M, int W, int H, int winsize, double* tmp /* 5 planes f64 */,

@@ -70,7 +70,7 @@ struct Plan {
     PolyConst pc{};
     PolyArgs pa{};                      // constants part filled once
     uint8_t* f0 = nullptr;              // device copy of a single frame (first frame of a shot / `prev`)
-    uint8_t* fstage[2] = {nullptr, nullptr};    // 2 x batch frames (host shots)
+    uint8_t* fstage[2] = {nullptr, nullptr};    // 2 x (2 * batch) frames: a chunk of a shot, or prev | next of a chunk of pairs
     float2* flow0[2] = {nullptr, nullptr};      // 2 x batch scale-0 flows
     uint8_t* bgr[2] = {nullptr, nullptr};       // 2 x batch pictures
     float* sums = nullptr;              // per-pair magnitude sums of a shot (host API), grown on demand
@@ -90,6 +90,7 @@ struct ofb_context {
     std::string err;
     Profiler prof;
     bool generic = false;
+    KernelOptions kopt;                 // per-context kernel options, copied into every Launch
     int batch = 0;                      // pairs per launch inside a shot (0 = choose from the frame size)
     int batch0 = 0;                     // pairs per launch at scale 0 (0 = same as batch)
     bool alt_order = false;             // alternate the grid direction of consecutive iteration launches (L2 reuse of M)
@@ -109,7 +110,9 @@ struct ofb_context {
 
 namespace {
 
-constexpr int MAX_BATCH = 64;
+constexpr int MAX_BATCH = 1024;        // pairs per launch; small frames (the 129-px feature regime) need hundreds to fill 148 SMs
+
+Launch make_launch(ofb_context* c, cudaStream_t s) { return Launch{s, &c->prof, c->device, c->sm_count, c->kopt}; }
 
 int fail(ofb_context* c, int code, const std::string& msg)
 {
@@ -123,6 +126,19 @@ int fail(ofb_context* c, int code, const std::string& msg)
         if (e_ != cudaSuccess)                                                                          \
             return fail(ctx, OFB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
+
+// Error paths of the host entry points return through CU() while asynchronous copies to or from CALLER-owned buffers may
+// still be queued: the guard drains the context's three streams before such a return hands the buffers back.
+struct DrainOnError {
+    ofb_context* c;
+    bool armed = true;
+    ~DrainOnError()
+    {
+        if (!armed) return;
+        cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_compute); cudaStreamSynchronize(c->s_d2h);
+        cudaGetLastError();
+    }
+};
 
 // ---- A.1 ------------------------------------------------------------------------------------
 int num_scales(int W, int H, double pyr_scale, int levels)
@@ -342,7 +358,7 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
     const size_t esz = dtype == OFB_U8 ? 1 : 4, n = (size_t)W * H;
     if (int rc = dalloc(ctx, pl, &pl.f0, n * esz)) return rc;
     for (int s = 0; s < 2; s++) {
-        if (int rc = dalloc(ctx, pl, &pl.fstage[s], B * n * esz)) return rc;
+        if (int rc = dalloc(ctx, pl, &pl.fstage[s], 2 * B * n * esz)) return rc;
         if (int rc = dalloc(ctx, pl, &pl.flow0[s], B * n)) return rc;
         if (int rc = dalloc(ctx, pl, &pl.bgr[s], B * n * 3)) return rc;
     }
@@ -458,7 +474,7 @@ bool solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                     if (gaussian) for (size_t q = 0; q < pl.gk.size() && q < 17; q++) a.gk[q] = pl.gk[q];
                     a.minmax = (fold_minmax && last && k == 0) ? ctx->minmax + 2 * z0 : nullptr;
                     a.reverse = (ctx->alt_order && (i % 2 == 0)) ? 1 : 0;     // um0 wrote M forwards; alternate from there
-                    launch_iter(L, a, p.winsize, !last, nb, ctx->sm_count);
+                    launch_iter(L, a, p.winsize, !last, nb);
                     cur ^= 1;
                 }
             }
@@ -522,7 +538,7 @@ int shot_batch(const ofb_context* ctx, int W, int H, int n_pairs)
     if (b <= 0) {
         double px = (double)W * H;
         b = (int)std::ceil(48.0e6 / px);
-        b = std::max(4, std::min(b, MAX_BATCH));
+        b = std::max(4, std::min(b, 512));
     }
     return std::max(1, std::min(b, std::min(n_pairs, MAX_BATCH)));
 }
@@ -657,7 +673,7 @@ int ofb_create(int device, ofb_context** out)
         return fail(nullptr, OFB_ERR_CUDA, m);
     }
     {
-        Launch L{c->s_compute, &c->prof};
+        Launch L = make_launch(c, c->s_compute);
         launch_build_hsv_table(L, c->hsv_table);
         if (cudaStreamSynchronize(c->s_compute) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
             delete c;
@@ -746,7 +762,7 @@ int ofb_farneback_device(ofb_context* ctx, const void* d_prev, const void* d_nex
     CU(cudaSetDevice(ctx->device));
     if (int rc = ensure_plan(ctx, W, H, dtype, p, 1)) return rc;
     size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4);
-    Launch L{ctx->s_compute, &ctx->prof};
+    Launch L = make_launch(ctx, ctx->s_compute);
     expand_frames(ctx, L, d_prev, 0, prev_pitch ? prev_pitch : row, 0, 1);
     expand_frames(ctx, L, d_next, 0, next_pitch ? next_pitch : row, 1, 1);
     solve_pairs(ctx, L, 0, 1, (float2*)d_flow, (size_t)W * H);
@@ -769,7 +785,7 @@ int ofb_farneback_host(ofb_context* ctx, const void* prev, const void* next, int
     size_t fbytes = sizeof(float2) * (size_t)W * H;
     if (p->flags & OFB_OPTFLOW_USE_INITIAL_FLOW) CU(cudaMemcpyAsync(pl.flow0[0], flow, fbytes, cudaMemcpyHostToDevice, s));
     size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4);
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     expand_frames(ctx, L, pl.f0, 0, row, 0, 1);
     expand_frames(ctx, L, pl.fstage[0], 0, row, 1, 1);
     solve_pairs(ctx, L, 0, 1, pl.flow0[0], (size_t)W * H);
@@ -784,7 +800,7 @@ int ofb_flow_to_bgr_device(ofb_context* ctx, const float* d_flow, int W, int H, 
 {
     if (!ctx || !d_flow || !d_bgr || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    Launch L{ctx->s_compute, &ctx->prof};
+    Launch L = make_launch(ctx, ctx->s_compute);
     picture(ctx, L, (const float2*)d_flow, 0, (size_t)W * H, d_bgr, 0, 1);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->s_compute));
@@ -801,7 +817,7 @@ int ofb_flow_to_bgr_host(ofb_context* ctx, const float* flow, int W, int H, uint
     if (int rc = stage_buf(ctx, 1, n * 3 + 16, &db)) return rc;
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     picture(ctx, L, (const float2*)df, 0, n, (uint8_t*)db, 0, 1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(bgr, db, n * 3, cudaMemcpyDeviceToHost, s));
@@ -813,7 +829,7 @@ int ofb_sum_magnitude_device(ofb_context* ctx, const float* d_flow, int W, int H
 {
     if (!ctx || !d_flow || !d_out || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
-    Launch L{ctx->s_compute, &ctx->prof};
+    Launch L = make_launch(ctx, ctx->s_compute);
     launch_sum_magnitude_batch(L, (const float2*)d_flow, 0, (size_t)W * H, ctx->sumacc, d_out, 1);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->s_compute));
@@ -829,7 +845,7 @@ int ofb_sum_magnitude_host(ofb_context* ctx, const float* flow, int W, int H, fl
     if (int rc = stage_buf(ctx, 0, n * 8, &df)) return rc;
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     launch_sum_magnitude_batch(L, (const float2*)df, 0, n, ctx->sumacc, ctx->sumout, 1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, ctx->sumout, 4, cudaMemcpyDeviceToHost, s));
@@ -848,7 +864,7 @@ int ofb_cart_to_polar_host(ofb_context* ctx, const float* flow, int W, int H, fl
     if (int rc = stage_buf(ctx, 2, n * 4, &da)) return rc;
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     launch_cart_to_polar(L, (const float2*)df, n, dm, da);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(mag, dm, n * 4, cudaMemcpyDeviceToHost, s));
@@ -871,7 +887,7 @@ int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtyp
     if (int rc = upload_frame(ctx, prev, 0, W, H, dtype, pl.f0, s)) return rc;
     if (int rc = upload_frame(ctx, next, 0, W, H, dtype, pl.fstage[0], s)) return rc;
     size_t row = (size_t)W * (dtype == OFB_U8 ? 1 : 4), n = (size_t)W * H;
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     expand_frames(ctx, L, pl.f0, 0, row, 0, 1);
     expand_frames(ctx, L, pl.fstage[0], 0, row, 1, 1);
     const bool mm = solve_pairs(ctx, L, 0, 1, pl.flow0[0], n, 1, bgr != nullptr);
@@ -882,43 +898,6 @@ int ofb_pair_host(ofb_context* ctx, const void* prev, const void* next, int dtyp
     if (magsum) CU(cudaMemcpyAsync(magsum, ctx->sumout, 4, cudaMemcpyDeviceToHost, s));
     if (flow) CU(cudaMemcpyAsync(flow, pl.flow0[0], n * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    return OFB_OK;
-}
-
-int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, int n_pairs, int W, int H,
-                   const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms)
-{
-    if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
-    if (!prev || !next || n_pairs < 1) return fail(ctx, OFB_ERR_BAD_ARG, "need at least one pair");
-    if (int rc = no_initial_flow(ctx, p)) return rc;
-    CU(cudaSetDevice(ctx->device));
-    const int B = shot_batch(ctx, W, H, n_pairs);
-    if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
-    Plan& pl = ctx->plan;
-    cudaStream_t s = ctx->s_compute;
-    const size_t n = (size_t)W * H;
-    float* d_sums = nullptr;
-    if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)n_pairs, &d_sums)) return rc;
-    Launch L{s, &ctx->prof};
-    CU(cudaEventRecord(ctx->ev_t0, s));
-    // chunk of b pairs: slots 2z <- prev[z], 2z+1 <- next[z]; one stream, the two staging buffers hold prev / next
-    for (int t0 = 0; t0 < n_pairs; t0 += B) {
-        const int b = std::min(B, n_pairs - t0);
-        CU(cudaMemcpyAsync(pl.fstage[0], prev + (size_t)t0 * n, (size_t)b * n, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(pl.fstage[1], next + (size_t)t0 * n, (size_t)b * n, cudaMemcpyHostToDevice, s));
-        expand_frames(ctx, L, pl.fstage[0], n, (size_t)W, 0, b, 2);     // prev[z] -> slot 2z
-        expand_frames(ctx, L, pl.fstage[1], n, (size_t)W, 1, b, 2);     // next[z] -> slot 2z+1
-        const bool mm = solve_pairs(ctx, L, 0, b, pl.flow0[0], n, 2, bgr != nullptr);
-        if (bgr) picture(ctx, L, pl.flow0[0], n, n, pl.bgr[0], n * 3, b, mm);
-        if (magsum) launch_sum_magnitude_batch(L, pl.flow0[0], n, n, ctx->sumacc, d_sums + t0, b);
-        CU(cudaGetLastError());
-        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[0], (size_t)b * n * 3, cudaMemcpyDeviceToHost, s));
-        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[0], (size_t)b * n * 8, cudaMemcpyDeviceToHost, s));
-    }
-    if (magsum) CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(ctx->ev_t1, s));
-    CU(cudaStreamSynchronize(s));
-    if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
     return OFB_OK;
 }
 
@@ -934,7 +913,7 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
     Plan& pl = ctx->plan;
     cudaStream_t s = ctx->s_compute;
     const size_t n = (size_t)W * H;
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     CU(cudaEventRecord(ctx->ev_t0, s));
     expand_frames(ctx, L, d_frames, n, (size_t)W, 0, 1);
     for (int t0 = 0; t0 + 1 < n_frames; t0 += B) {
@@ -952,16 +931,24 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
     return OFB_OK;
 }
 
-// Shared body of ofb_shot_host (sW = 0: frames are gray, W x H) and ofb_shot_bgr_host (frames are decoded BGR frames of
-// sW x sH; the gray frames of W x H are produced on the GPU, optionally returned through gray_out).
-static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, int sW, int sH, const ofb_params* p,
-                          uint8_t* bgr, float* magsum, float* flow, uint8_t* gray_out, float* device_ms)
+// Shared body of the four host entry points.
+//   shot  (next == nullptr): `first` holds n_pairs+1 consecutive frames; pair t = frames t, t+1; a frame is expanded once.
+//   pairs (next != nullptr): pair t = (first[t], next[t]), independent frames (the window loop of optical_flow.py:83-99).
+//   sW > 0: the frames are decoded BGR frames of sW x sH; gray frames of W x H are produced on the GPU (gray_out: shot only).
+// Three streams: frames of chunk c+1 upload (s_h2d) while chunk c computes (s_compute) and the results of chunk c-1 download
+// (s_d2h); staging buffers are double-buffered by chunk parity and guarded by events, no host synchronisation inside.
+//   fptr != nullptr (shot only): frame i lives at fptr[i] (a decoder's own buffers; nothing is assembled on the host).
+static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next, int n_pairs, int W, int H, int sW, int sH,
+                     const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, uint8_t* gray_out, float* device_ms,
+                     const uint8_t* const* fptr = nullptr)
 {
+    if (fptr && !first) first = fptr[0];
     if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
-    if (!frames || n_frames < 2) return fail(ctx, OFB_ERR_BAD_ARG, "need at least two frames");
+    const bool pairs = next != nullptr;
+    if (!first || n_pairs < 1) return fail(ctx, OFB_ERR_BAD_ARG, pairs ? "need at least one pair" : "need at least two frames");
     if (int rc = no_initial_flow(ctx, p)) return rc;
     CU(cudaSetDevice(ctx->device));
-    const int B = shot_batch(ctx, W, H, n_frames - 1);
+    const int B = shot_batch(ctx, W, H, n_pairs);
     if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t sc = ctx->s_compute, su = ctx->s_h2d, sd = ctx->s_d2h;
@@ -969,17 +956,18 @@ static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames,
     const bool from_bgr = sW > 0;
     const size_t sn = from_bgr ? (size_t)sW * sH * 3 : n;                // bytes of one source frame
     float* d_sums = nullptr;
-    if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)(n_frames - 1), &d_sums)) return rc;
-    uint8_t *bs0 = nullptr, *bs[2] = {nullptr, nullptr};                   // BGR staging: first frame, two chunks
+    if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)n_pairs, &d_sums)) return rc;
+    // BGR staging: [first frame of a shot] [parity 0: B + B frames] [parity 1: B + B frames]
+    uint8_t *bs0 = nullptr, *bs[2] = {nullptr, nullptr};
+    const size_t sna = (sn + 15) & ~(size_t)15;
     if (from_bgr) {
         float* q;
-        const size_t sna = (sn + 15) & ~(size_t)15;
-        if (int rc = stage_buf(ctx, 4, sna * (2 * (size_t)B + 1), &q)) return rc;
-        bs0 = (uint8_t*)q; bs[0] = bs0 + sna; bs[1] = bs[0] + sna * B;
+        if (int rc = stage_buf(ctx, 4, sna * (4 * (size_t)B + 1), &q)) return rc;
+        bs0 = (uint8_t*)q; bs[0] = bs0 + sna; bs[1] = bs[0] + sna * 2 * B;
     }
-    Launch L{sc, &ctx->prof};
-    const int n_pairs = n_frames - 1;
-    // Chunk schedule: full chunks of B pairs, but a long shot starts and ends with short ones (B/4, B/2, ..., B/2, B/4):
+    Launch L = make_launch(ctx, sc);
+    DrainOnError drain{ctx};
+    // Chunk schedule: full chunks of B pairs, but a long job starts and ends with short ones (B/4, B/2, ..., B/2, B/4):
     // the first upload and the last download are the only copies that nothing overlaps, so they are kept small.
     std::vector<int> cstart;                                              // first pair of every chunk, then n_pairs
     {
@@ -993,16 +981,24 @@ static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames,
         cstart.push_back(n_pairs);
     }
     const int n_chunks = (int)cstart.size() - 1;
+    // where the source frames of a chunk land on the device: `lo` = frames t0+1.. (shot) or prev (pairs), `hi` = next (pairs)
+    auto src_lo = [&](int par) { return from_bgr ? bs[par] : pl.fstage[par]; };
+    auto src_hi = [&](int par) { return from_bgr ? bs[par] + sna * B : pl.fstage[par] + n * B; };
 
     CU(cudaEventRecord(ctx->ev_t0, su));
-    // Uploads run ahead on s_h2d (frames of chunk c go to fstage[c & 1]), results drain on s_d2h
-    // (pictures / flows of chunk c sit in bgr[c & 1] / flow0[c & 1]); the compute stream only waits on
-    // the events it needs, so H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c.
-    CU(cudaMemcpyAsync(from_bgr ? bs0 : pl.f0, frames, sn, cudaMemcpyHostToDevice, su));
+    if (!pairs) CU(cudaMemcpyAsync(from_bgr ? bs0 : pl.f0, first, sn, cudaMemcpyHostToDevice, su));
     auto upload = [&](int c) -> int {
         const int t0 = cstart[c], b = cstart[c + 1] - t0, par = c & 1;
         if (c >= 2) CU(cudaStreamWaitEvent(su, ctx->ev_frame_free[par], 0));
-        CU(cudaMemcpyAsync(from_bgr ? bs[par] : pl.fstage[par], frames + (size_t)(t0 + 1) * sn, (size_t)b * sn, cudaMemcpyHostToDevice, su));
+        if (pairs) {
+            CU(cudaMemcpyAsync(src_lo(par), first + (size_t)t0 * sn, (size_t)b * sn, cudaMemcpyHostToDevice, su));
+            CU(cudaMemcpyAsync(src_hi(par), next + (size_t)t0 * sn, (size_t)b * sn, cudaMemcpyHostToDevice, su));
+        } else if (fptr) {
+            for (int i = 0; i < b; i++)
+                CU(cudaMemcpyAsync(src_lo(par) + (size_t)i * sn, fptr[t0 + 1 + i], sn, cudaMemcpyHostToDevice, su));
+        } else {
+            CU(cudaMemcpyAsync(src_lo(par), first + (size_t)(t0 + 1) * sn, (size_t)b * sn, cudaMemcpyHostToDevice, su));
+        }
         CU(cudaEventRecord(ctx->ev_h2d[par], su));
         return 0;
     };
@@ -1011,33 +1007,48 @@ static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames,
         const int t0 = cstart[c], b = cstart[c + 1] - t0, par = c & 1;
         if (c + 1 < n_chunks) if (int rc = upload(c + 1)) return rc;
         CU(cudaStreamWaitEvent(sc, ctx->ev_h2d[par], 0));
+        uint8_t* g_lo = pl.fstage[par];
+        uint8_t* g_hi = pl.fstage[par] + n * B;
         if (from_bgr) {
-            if (c == 0) preprocess_frames(ctx, L, bs0, sn, sW, sH, pl.f0, n, W, H, 1);
-            preprocess_frames(ctx, L, bs[par], sn, sW, sH, pl.fstage[par], n, W, H, b);
-            if (gray_out) {          // the gray frames the reference would have computed on the host (stream-ordered copy)
+            if (!pairs && c == 0) preprocess_frames(ctx, L, bs0, sn, sW, sH, pl.f0, n, W, H, 1);
+            preprocess_frames(ctx, L, bs[par], sn, sW, sH, g_lo, n, W, H, b);
+            if (pairs) preprocess_frames(ctx, L, bs[par] + sna * B, sn, sW, sH, g_hi, n, W, H, b);
+            if (gray_out && !pairs) {   // the gray frames the reference would have computed on the host (stream-ordered copy)
                 if (c == 0) CU(cudaMemcpyAsync(gray_out, pl.f0, n, cudaMemcpyDeviceToHost, sc));
-                CU(cudaMemcpyAsync(gray_out + (size_t)(t0 + 1) * n, pl.fstage[par], (size_t)b * n, cudaMemcpyDeviceToHost, sc));
+                CU(cudaMemcpyAsync(gray_out + (size_t)(t0 + 1) * n, g_lo, (size_t)b * n, cudaMemcpyDeviceToHost, sc));
             }
         }
-        if (c == 0) expand_frames(ctx, L, pl.f0, n, (size_t)W, 0, 1);
-        expand_frames(ctx, L, pl.fstage[par], n, (size_t)W, t0 + 1, b);
+        if (pairs) {
+            expand_frames(ctx, L, g_lo, n, (size_t)W, 0, b, 2);           // prev[z] -> slot 2z
+            expand_frames(ctx, L, g_hi, n, (size_t)W, 1, b, 2);           // next[z] -> slot 2z+1
+        } else {
+            if (c == 0) expand_frames(ctx, L, pl.f0, n, (size_t)W, 0, 1);
+            expand_frames(ctx, L, g_lo, n, (size_t)W, t0 + 1, b);
+        }
         CU(cudaEventRecord(ctx->ev_frame_free[par], sc));
         if (c >= 2) CU(cudaStreamWaitEvent(sc, ctx->ev_out_free[par], 0));
-        const bool mm = solve_pairs(ctx, L, t0, b, pl.flow0[par], n, 1, bgr != nullptr);
+        const bool mm = pairs ? solve_pairs(ctx, L, 0, b, pl.flow0[par], n, 2, bgr != nullptr)
+                              : solve_pairs(ctx, L, t0, b, pl.flow0[par], n, 1, bgr != nullptr);
         if (bgr) picture(ctx, L, pl.flow0[par], n, n, pl.bgr[par], n * 3, b, mm);
         if (magsum) launch_sum_magnitude_batch(L, pl.flow0[par], n, n, ctx->sumacc, d_sums + t0, b);
         CU(cudaEventRecord(ctx->ev_out_ready[par], sc));
-        CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
-        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[par], (size_t)b * n * 3, cudaMemcpyDeviceToHost, sd));
-        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[par], (size_t)b * n * 8, cudaMemcpyDeviceToHost, sd));
-        CU(cudaEventRecord(ctx->ev_out_free[par], sd));
+        if (bgr || flow) {
+            CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
+            if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[par], (size_t)b * n * 3, cudaMemcpyDeviceToHost, sd));
+            if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[par], (size_t)b * n * 8, cudaMemcpyDeviceToHost, sd));
+            CU(cudaEventRecord(ctx->ev_out_free[par], sd));
+        } else {
+            CU(cudaEventRecord(ctx->ev_out_free[par], sc));
+        }
     }
+    CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[(n_chunks - 1) & 1], 0));
     if (magsum) CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost, sd));
     CU(cudaEventRecord(ctx->ev_t1, sd));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(sd));
     CU(cudaStreamSynchronize(sc));
     CU(cudaStreamSynchronize(su));
+    drain.armed = false;
     if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
     return OFB_OK;
 }
@@ -1045,7 +1056,22 @@ static int shot_host_impl(ofb_context* ctx, const uint8_t* frames, int n_frames,
 int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p,
                   uint8_t* bgr, float* magsum, float* flow, float* device_ms)
 {
-    return shot_host_impl(ctx, frames, n_frames, W, H, 0, 0, p, bgr, magsum, flow, nullptr, device_ms);
+    return host_impl(ctx, frames, nullptr, n_frames - 1, W, H, 0, 0, p, bgr, magsum, flow, nullptr, device_ms);
+}
+
+int ofb_shot_host_v(ofb_context* ctx, const uint8_t* const* frames, int n_frames, int W, int H, const ofb_params* p,
+                    uint8_t* bgr, float* magsum, float* flow, float* device_ms)
+{
+    if (!frames) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer table");
+    for (int i = 0; i < n_frames; i++) if (!frames[i]) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer");
+    return host_impl(ctx, nullptr, nullptr, n_frames - 1, W, H, 0, 0, p, bgr, magsum, flow, nullptr, device_ms, frames);
+}
+
+int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, int n_pairs, int W, int H,
+                   const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms)
+{
+    if (!next) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer");
+    return host_impl(ctx, prev, next, n_pairs, W, H, 0, 0, p, bgr, magsum, flow, nullptr, device_ms);
 }
 
 int ofb_shot_bgr_host(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames, int W, int H, int dW, int dH,
@@ -1054,50 +1080,17 @@ int ofb_shot_bgr_host(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames,
     if (!ctx) return OFB_ERR_BAD_ARG;
     CU(cudaSetDevice(ctx->device));
     if (int rc = bgr_geometry(ctx, W, H, &dW, &dH)) return rc;
-    return shot_host_impl(ctx, bgr_frames, n_frames, dW, dH, W, H, p, bgr, magsum, flow, gray, device_ms);
+    return host_impl(ctx, bgr_frames, nullptr, n_frames - 1, dW, dH, W, H, p, bgr, magsum, flow, gray, device_ms);
 }
 
 int ofb_pairs_bgr_host(ofb_context* ctx, const uint8_t* prev_bgr, const uint8_t* next_bgr, int n_pairs, int W, int H, int dW, int dH,
                        const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms)
 {
     if (!ctx) return OFB_ERR_BAD_ARG;
+    if (!next_bgr) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer");
     CU(cudaSetDevice(ctx->device));
     if (int rc = bgr_geometry(ctx, W, H, &dW, &dH)) return rc;
-    if (int rc = validate(ctx, dW, dH, OFB_U8, p)) return rc;
-    if (!prev_bgr || !next_bgr || n_pairs < 1) return fail(ctx, OFB_ERR_BAD_ARG, "need at least one pair");
-    if (int rc = no_initial_flow(ctx, p)) return rc;
-    const int B = shot_batch(ctx, dW, dH, n_pairs);
-    if (int rc = ensure_plan(ctx, dW, dH, OFB_U8, p, B)) return rc;
-    Plan& pl = ctx->plan;
-    cudaStream_t s = ctx->s_compute;
-    const size_t n = (size_t)dW * dH, sn = (size_t)W * H * 3;
-    float* d_sums = nullptr;
-    if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)n_pairs, &d_sums)) return rc;
-    float* q;
-    if (int rc = stage_buf(ctx, 4, sn * 2 * (size_t)B + 32, &q)) return rc;
-    uint8_t* bs[2] = {(uint8_t*)q, (uint8_t*)q + ((sn * B + 15) & ~(size_t)15)};
-    Launch L{s, &ctx->prof};
-    CU(cudaEventRecord(ctx->ev_t0, s));
-    for (int t0 = 0; t0 < n_pairs; t0 += B) {
-        const int b = std::min(B, n_pairs - t0);
-        CU(cudaMemcpyAsync(bs[0], prev_bgr + (size_t)t0 * sn, (size_t)b * sn, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(bs[1], next_bgr + (size_t)t0 * sn, (size_t)b * sn, cudaMemcpyHostToDevice, s));
-        preprocess_frames(ctx, L, bs[0], sn, W, H, pl.fstage[0], n, dW, dH, b);
-        preprocess_frames(ctx, L, bs[1], sn, W, H, pl.fstage[1], n, dW, dH, b);
-        expand_frames(ctx, L, pl.fstage[0], n, (size_t)dW, 0, b, 2);     // prev[z] -> slot 2z
-        expand_frames(ctx, L, pl.fstage[1], n, (size_t)dW, 1, b, 2);     // next[z] -> slot 2z+1
-        const bool mm = solve_pairs(ctx, L, 0, b, pl.flow0[0], n, 2, bgr != nullptr);
-        if (bgr) picture(ctx, L, pl.flow0[0], n, n, pl.bgr[0], n * 3, b, mm);
-        if (magsum) launch_sum_magnitude_batch(L, pl.flow0[0], n, n, ctx->sumacc, d_sums + t0, b);
-        CU(cudaGetLastError());
-        if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[0], (size_t)b * n * 3, cudaMemcpyDeviceToHost, s));
-        if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[0], (size_t)b * n * 8, cudaMemcpyDeviceToHost, s));
-    }
-    if (magsum) CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(ctx->ev_t1, s));
-    CU(cudaStreamSynchronize(s));
-    if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
-    return OFB_OK;
+    return host_impl(ctx, prev_bgr, next_bgr, n_pairs, dW, dH, W, H, p, bgr, magsum, flow, nullptr, device_ms);
 }
 
 // ---- frame preprocessing on its own (parity tests) ---------------------------------------------
@@ -1111,7 +1104,7 @@ int ofb_bgr_to_gray_host(ofb_context* ctx, const uint8_t* bgr, int W, int H, uin
     if (int rc = stage_buf(ctx, 1, n + 16, &dd)) return rc;
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(ds, bgr, n * 3, cudaMemcpyHostToDevice, s));
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     launch_bgr2gray(L, (const uint8_t*)ds, 0, (size_t)W * 3, (uint8_t*)dd, 0, (size_t)W, W, H, 1);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(gray, dd, n, cudaMemcpyDeviceToHost, s));
@@ -1131,7 +1124,7 @@ int ofb_resize_u8_host(ofb_context* ctx, const uint8_t* src, int W, int H, int c
     if (int rc = stage_buf(ctx, 1, dn + 16, &dd)) return rc;
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(ds, src, sn, cudaMemcpyHostToDevice, s));
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     launch_resize_u8(L, (const uint8_t*)ds, 0, (size_t)W * channels, channels, to_gray != 0, (uint8_t*)dd, 0,
                      (size_t)dW * (to_gray ? 1 : channels), dW, dH, ctx->rs, 1);
     CU(cudaGetLastError());
@@ -1180,7 +1173,7 @@ int ofb_stage_level_image(ofb_context* ctx, const void* frame, int dtype, int W,
     CU(cudaMemcpyAsync(dtab + o_ay, wy.data(), 4 * wy.size(), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(dfr, frame, (size_t)W * H * esz, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));      // host vectors go out of scope below
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     if (ctx->generic) {
         launch_pyr_h(L, dfr, dtype, W, H, (size_t)W * esz, dtab + o_taps, ksize, dT, Wk, pitch);
         launch_pyr_v(L, dT, H, pitch, dtab + o_taps, ksize, dI, Wk, Hk, pitch);
@@ -1219,7 +1212,7 @@ int ofb_stage_polyexp(ofb_context* ctx, const float* img, int W, int H, int poly
     CU(cudaStreamSynchronize(s));
     int len = 2 * poly_n + 1;
     PolyConst pc{dtab, dtab + len, dtab + 2 * len, poly_n, ig[0], ig[1], ig[2], ig[3]};
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     RView Rp{reinterpret_cast<float4*>(dR), dR + 4 * plane, pitch};
     if (!ctx->generic && polyexp2_supported(poly_n)) {
         PolyArgs a;
@@ -1249,7 +1242,7 @@ int ofb_stage_update_matrices(ofb_context* ctx, const float* R0, const float* R1
     if (int rc = stage_buf(ctx, 3, sizeof(float) * 5 * plane, &dM)) return rc;
     if (int rc = stage_buf(ctx, 4, sizeof(float) * 2 * n, &dfl)) return rc;
     cudaStream_t s = ctx->s_compute;
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     RView p0{reinterpret_cast<float4*>(dR), dR + 4 * plane, pitch};
     RView p1{reinterpret_cast<float4*>(dR + 5 * plane), dR + 9 * plane, pitch};
     Planes5 pm{dM, plane, pitch};
@@ -1289,7 +1282,7 @@ int ofb_stage_blur_solve(ofb_context* ctx, const float* M, int W, int H, int win
     gauss_half_taps(winsize, gk);
     if (int rc = stage_buf(ctx, 4, sizeof(float) * gk.size(), &dk)) return rc;
     cudaStream_t s = ctx->s_compute;
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     Planes5 pm{dM, plane, pitch};
     CU(cudaMemcpyAsync(dk, gk.data(), sizeof(float) * gk.size(), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(din, M, sizeof(float) * 5 * n, cudaMemcpyHostToDevice, s));
@@ -1302,7 +1295,7 @@ int ofb_stage_blur_solve(ofb_context* ctx, const float* M, int W, int H, int win
         a.c = gaussian ? 1e-3f : (float)(1e-3 * (double)winsize * winsize * winsize * winsize);
         a.gauss = gaussian ? 1 : 0;
         if (gaussian) for (size_t q = 0; q < gk.size() && q < 17; q++) a.gk[q] = gk[q];
-        launch_iter(L, a, winsize, false, 1, ctx->sm_count);
+        launch_iter(L, a, winsize, false, 1);
     } else if (gaussian) {
         launch_blur_solve_gauss(L, pm, W, H, winsize, dk, dtmp, (float2*)dfl, true);
     } else {
@@ -1322,7 +1315,7 @@ int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, in
     if (int rc = stage_buf(ctx, 0, sizeof(float) * 2 * (size_t)Wp * Hp, &dp)) return rc;
     if (int rc = stage_buf(ctx, 1, sizeof(float) * 2 * (size_t)W * H, &df)) return rc;
     cudaStream_t s = ctx->s_compute;
-    Launch L{s, &ctx->prof};
+    Launch L = make_launch(ctx, s);
     CU(cudaMemcpyAsync(dp, prev_flow, sizeof(float) * 2 * (size_t)Wp * Hp, cudaMemcpyHostToDevice, s));
     launch_upsample_flow(L, (const float2*)dp, Wp, Hp, (float2*)df, W, H, (float)(1. / pyr_scale));
     CU(cudaGetLastError());
@@ -1337,9 +1330,9 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!ctx || !name) return OFB_ERR_BAD_ARG;
     if (!strcmp(name, "generic_kernels")) { ctx->generic = value != 0; return OFB_OK; }
     if (!strcmp(name, "alt_order")) { ctx->alt_order = value != 0; return OFB_OK; }
-    if (!strcmp(name, "iter_ilp")) { set_iter_ilp(value); return OFB_OK; }
-    if (!strcmp(name, "iter_prefetch")) { set_iter_prefetch(value); return OFB_OK; }
-    if (!strcmp(name, "polyexp_tma")) { set_polyexp_tma(value); return OFB_OK; }
+    if (!strcmp(name, "iter_ilp")) { ctx->kopt.iter_ilp = value; return OFB_OK; }
+    if (!strcmp(name, "iter_prefetch")) { ctx->kopt.iter_prefetch = value; return OFB_OK; }
+    if (!strcmp(name, "polyexp_tma")) { ctx->kopt.polyexp_tma = value; return OFB_OK; }
     if (!strcmp(name, "hsv_table")) { ctx->use_hsv_table = value != 0; return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }

@@ -346,21 +346,14 @@ k_iter(IterArgs a)
     }
 }
 
-static int g_iter_ilp = 1;
-void set_iter_ilp(int v) { g_iter_ilp = v; }
-static int g_iter_prefetch = 1;
-void set_iter_prefetch(int v) { g_iter_prefetch = v; }
-
 template <int M, bool FUSE, int ILP, bool GAUSS>
-static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
+static void run_iter(Launch& L, IterArgs a, int batch)
 {
     constexpr int R = 2 * M + 1, TW = IT_CW - 2 * M, HP = TW + 1;
     const size_t smem = sizeof(float) * (5 * R * IT_VP + 5 * R * HP);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_iter<M, FUSE, ILP, GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    static unsigned long long configured = 0;             // bit d: attribute set on device d
+    L.dyn_smem(k_iter<M, FUSE, ILP, GAUSS>, smem, configured);
+    const int sm_count = L.sm_count;
     const int xt = divup(a.W, TW);
     // aim at ~1 CTA per SM for ONE pair; strips are whole steps of R rows.  The partition must not depend
     // on the batch size: the van Herk blocks restart at strip boundaries, so it fixes the f32 rounding, and a
@@ -370,7 +363,7 @@ static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
     strip = std::max(strip, std::min(a.H, 4 * R));          // the block-A preload of a strip costs one step: keep it <= 25 %
     strip = divup(strip, R) * R;
     a.strip_rows = strip;
-    a.prefetch = g_iter_prefetch;
+    a.prefetch = L.opt.iter_prefetch;
     dim3 grid(batch, xt, divup(a.H, strip));
     L.run(GAUSS ? (FUSE ? "iter_fused_gauss" : "iter_last_gauss") : (FUSE ? "iter_fused" : "iter_last"), [&](cudaStream_t s) {
         k_iter<M, FUSE, ILP, GAUSS><<<grid, IT_THREADS, smem, s>>>(a);
@@ -380,15 +373,15 @@ static void run_iter(Launch& L, IterArgs a, int batch, int sm_count)
 bool iter_supported(int winsize) { int m = winsize / 2; return m >= 1 && m <= 16; }
 
 
-void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch, int sm_count)
+void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch)
 {
     const int m = winsize / 2;
     if (a.gauss) {
         switch (m) {
 #define OFB_CASE(MM)                                                                          \
     case MM:                                                                                  \
-        if (!fuse_um) run_iter<MM, false, 1, true>(L, a, batch, sm_count);                    \
-        else run_iter<MM, true, 1, true>(L, a, batch, sm_count);                              \
+        if (!fuse_um) run_iter<MM, false, 1, true>(L, a, batch);                    \
+        else run_iter<MM, true, 1, true>(L, a, batch);                              \
         return;
             OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
             OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)
@@ -399,10 +392,10 @@ void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int ba
     switch (m) {
 #define OFB_CASE(MM)                                                                          \
     case MM:                                                                                  \
-        if (!fuse_um) run_iter<MM, false, 1, false>(L, a, batch, sm_count);                   \
-        else if (g_iter_ilp >= 3) run_iter<MM, true, 3, false>(L, a, batch, sm_count);        \
-        else if (g_iter_ilp == 2) run_iter<MM, true, 2, false>(L, a, batch, sm_count);        \
-        else run_iter<MM, true, 1, false>(L, a, batch, sm_count);                             \
+        if (!fuse_um) run_iter<MM, false, 1, false>(L, a, batch);                   \
+        else if (L.opt.iter_ilp >= 3) run_iter<MM, true, 3, false>(L, a, batch);        \
+        else if (L.opt.iter_ilp == 2) run_iter<MM, true, 2, false>(L, a, batch);        \
+        else run_iter<MM, true, 1, false>(L, a, batch);                             \
         return;
         OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
         OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)

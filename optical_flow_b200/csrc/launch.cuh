@@ -52,9 +52,30 @@ struct Profiler {
     }
 };
 
+// Per-context kernel options (ofb_set_option), carried by every Launch: nothing about a launch is process-global,
+// so two contexts (two devices, or two host threads) never see each other's settings.
+struct KernelOptions {
+    int iter_ilp = 1;          // pixels whose UpdateMatrices gathers a k_iter thread keeps in flight
+    int iter_prefetch = 1;     // software L2 prefetch one step ahead in k_iter
+    int polyexp_tma = 0;       // persistent TMA variant of the scale-0 polynomial expansion
+};
+
 struct Launch {
     cudaStream_t stream;
     Profiler* prof;
+    int device = 0;            // device the stream belongs to (function attributes are per device)
+    int sm_count = 148;
+    KernelOptions opt{};
+
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: remember, per kernel
+    // instance (`done` is a static of the calling template), which devices have been configured.
+    template <class K> void dyn_smem(K kernel, size_t bytes, unsigned long long& done) const
+    {
+        const unsigned long long bit = 1ull << (device & 63);
+        if (done & bit) return;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        done |= bit;
+    }
     template <class F> void run(const char* name, F&& f)
     {
         int id = prof->id_of(name);

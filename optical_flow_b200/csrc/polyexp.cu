@@ -573,8 +573,6 @@ k_polyexp2_tma(const __grid_constant__ CUtensorMap tmap, PolyArgs a, int tiles_x
 // 300-pair step against 8.4 ms for the one-tile-per-CTA kernel -- the staging latency it hides (~15 % of the kernel) is
 // smaller than what the persistent loop adds (tile decode, barrier wait, spills around the f64 pass), so it is kept
 // as a tested alternative (tests/test_gpu_parity.py::test_polyexp_tma_path_is_bit_identical), not as the default.
-static int g_polyexp_tma = 0;
-void set_polyexp_tma(int v) { g_polyexp_tma = v; }
 
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -586,9 +584,8 @@ template <int N>
 static bool run_polyexp2_tma(Launch& L, const PolyArgs& a, int batch)
 {
     using G = PeTma<N>;
-    if (!g_polyexp_tma || (a.W & 15) || (a.src_pitch & 15) || (a.src_item & 15) || ((uintptr_t)a.src & 15) || a.W < 16) return false;
+    if (!L.opt.polyexp_tma || (a.W & 15) || (a.src_pitch & 15) || (a.src_item & 15) || ((uintptr_t)a.src & 15) || a.W < 16) return false;
     static PFN_tensorMapEncodeTiled encode = nullptr;
-    static int sms = 0;
     static bool tried = false;
     if (!tried) {
         tried = true;
@@ -598,11 +595,10 @@ static bool run_polyexp2_tma(Launch& L, const PolyArgs& a, int batch)
             encode = (PFN_tensorMapEncodeTiled)fn;
         else
             cudaGetLastError();
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_polyexp2_tma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     }
+    static unsigned long long configured = 0;
+    L.dyn_smem(k_polyexp2_tma<N>, G::SMEM, configured);
+    const int sms = L.sm_count;
     if (!encode || sms <= 0) return false;
     CUtensorMap tm;
     const cuuint64_t gdim[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)batch};
@@ -625,11 +621,8 @@ static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
     constexpr int TW = PE_TW, TH = PE_TH, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1);
     size_t smem = sizeof(double) * 3 * TH * RP +
                   sizeof(float) * (SRC == 0 ? (size_t)0 : (size_t)(PH + 2) * (PW + 2) + (size_t)(PH + 2) * PW);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_polyexp2<N, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    static unsigned long long configured = 0;
+    L.dyn_smem(k_polyexp2<N, SRC>, smem, configured);
     dim3 grid(divup(a.W, TW), divup(a.H, TH), batch);
     const char* nm = SRC == 0 ? "polyexp_level" : "polyexp_scale0";
     L.run(nm, [&](cudaStream_t s) { k_polyexp2<N, SRC><<<grid, PE_THREADS, smem, s>>>(a); });

@@ -224,6 +224,28 @@ class Farneback:
                                           C.byref(dev_ms)))
         return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
 
+    def shot_frames(self, frame_list, want_bgr=True, want_magsum=False, want_flow=False, out_bgr=None, **params):
+        """`shot` for frames that live in separate buffers (what a decoder hands out): a sequence of (H, W) uint8
+        C-contiguous arrays.  No host-side assembly -- each frame is uploaded from where it lies (ofb_shot_host_v)."""
+        n = len(frame_list)
+        if n < 2:
+            raise ValueError("need at least two frames")
+        H, W = frame_list[0].shape
+        for f in frame_list:
+            if f.shape != (H, W) or f.dtype != np.uint8 or not f.flags.c_contiguous:
+                raise ValueError("every frame must be a C-contiguous (H, W) uint8 array of the same size")
+        table = (C.c_void_p * n)(*[f.ctypes.data for f in frame_list])
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        bgr = None
+        if want_bgr:
+            bgr = out_bgr if out_bgr is not None else np.empty((n - 1, H, W, 3), np.uint8)
+            assert bgr.shape[0] >= n - 1 and bgr.shape[1:] == (H, W, 3) and bgr.dtype == np.uint8 and bgr.flags.c_contiguous
+        ms = np.zeros(n - 1, np.float32) if want_magsum else None
+        fl = np.empty((n - 1, H, W, 2), np.float32) if want_flow else None
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_shot_host_v(self._h, table, n, W, H, C.byref(prm), _ptr(bgr), _ptr(ms), _ptr(fl), C.byref(dev_ms)))
+        return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
+
     def pairs(self, prev_frames, next_frames, want_bgr=False, want_magsum=True, want_flow=False, **params):
         """n independent pairs (prev_frames[i], next_frames[i]) in one batched submission: the window loop of
         optical_flow.py:83-99 (its pairs need not share frames)."""

