@@ -487,7 +487,7 @@ def run_shot(args, rank, local_rank, world):
             lat = latency_leg(eng, frames, W, H)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            ntasks = max(8 * cores, 64) if W * H <= 1920 * 1080 else max(2 * cores, 8)
+            ntasks = max(24 * cores, 64) if W * H <= 1920 * 1080 else max(4 * cores, 8)
             r, kind, ver, dt = cpu_reference_rate(np.array(frames[:9]), ntasks, cores)
             cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": "%d pairs of the same %dx%d shot in %.1f s, %d processes x cv2.setNumThreads(1); %s; %s"

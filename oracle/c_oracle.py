@@ -19,7 +19,7 @@ OPTFLOW_FARNEBACK_GAUSSIAN = 256
 
 def build(force=False):
     """Compile the C oracle with gcc (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "preprocess_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("farneback_oracle.c", "preprocess_oracle.c", "jpeg_oracle.c")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -264,3 +264,40 @@ def resize_u8(src, dsize):
     out = np.empty((dH, dW) if src.ndim == 2 else (dH, dW, cn), np.uint8)
     lib().orc_resize_u8(_u8(src), W, H, cn, _u8(out), dW, dH)
     return out
+
+
+# ---- the JPEG artefact (visualize_optical_flow.py:57-58; oracle/jpeg_oracle.c) -----------------------------------
+def jpeg_encode(bgr, quality=95):
+    """cv2.imencode('.jpeg', bgr)[1] for an (H, W, 3) uint8 picture with cv2's defaults (quality 95, 4:2:0, standard tables)."""
+    bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+    H, W = bgr.shape[:2]
+    L = lib()
+    L.jpeg_oracle_encode.restype = C.c_size_t
+    L.jpeg_oracle_encode.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_size_t]
+    cap = W * H * 4 + 4096
+    out = np.empty(cap, np.uint8)
+    n = L.jpeg_oracle_encode(_u8(bgr), W, H, int(quality), _u8(out), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def jpeg_coefficients(bgr, quality=95):
+    """Quantised DCT coefficients in scan order: (mcu_rows * mcu_cols, 6, 64) int16, zigzag order inside a block."""
+    bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+    H, W = bgr.shape[:2]
+    n_mcu = ((W + 15) // 16) * ((H + 15) // 16)
+    out = np.empty((n_mcu, 6, 64), np.int16)
+    L = lib()
+    L.jpeg_oracle_coefficients.restype = None
+    L.jpeg_oracle_coefficients.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int16)]
+    L.jpeg_oracle_coefficients(_u8(bgr), W, H, int(quality), out.ctypes.data_as(C.POINTER(C.c_int16)))
+    return out
+
+
+def jpeg_header(W, H, quality=95):
+    L = lib()
+    L.jpeg_oracle_header.restype = C.c_size_t
+    L.jpeg_oracle_header.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    out = np.empty(1024, np.uint8)
+    n = L.jpeg_oracle_header(W, H, int(quality), _u8(out))
+    return out[:n].copy()
