@@ -17,6 +17,8 @@
  *                         the loop body                                visualize_optical_flow.py:37-55 (picture)
  *   ofb_shot_*            the sequential per-pair loops                visualize_optical_flow.py:21-63,
  *                                                                      optical_flow.py:83-99
+ *   ofb_*_jpeg            cv2.imwrite(os.path.join(images_path, 'flow_<ms>.jpeg'), rgb)   visualize_optical_flow.py:57-58
+ *                         (the encoder behind it: libjpeg baseline, quality 95, 4:2:0 -- the same bytes, made on the GPU)
  *   ofb_bgr_to_gray_*     cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)      optical_flow.py:44,
  *                                                                      visualize_optical_flow.py:31,35
  *   ofb_resize_u8_*       cv2.resize(frame, (w, h))  [INTER_LINEAR]    optical_flow.py:25-31
@@ -123,6 +125,19 @@ int ofb_shot_host(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, 
  * frames[i], W*H bytes.  Nothing is assembled on the host; every frame is uploaded straight from where it lies. */
 int ofb_shot_host_v(ofb_context* ctx, const uint8_t* const* frames, int n_frames, int W, int H, const ofb_params* p,
                     uint8_t* bgr, float* magsum, float* flow, float* device_ms);
+/* ofb_shot_host whose pictures leave the GPU as JPEG files instead of raw BGR (visualize_optical_flow.py:57-58): the byte
+ * streams cv2.imwrite(..., rgb) / cv2.imencode('.jpeg', rgb) produce for the same picture (baseline, `quality` as
+ * IMWRITE_JPEG_QUALITY, cv2's default is 95; 4:2:0; standard Huffman tables), byte for byte.  The n_frames-1 streams are
+ * written back to back into `jpeg` (capacity jpeg_cap bytes; OFB_ERR_BAD_ARG if it is too small), jpeg_sizes[i] = bytes of
+ * stream i (stream i starts at the sum of the sizes before it).  magsum may be NULL. */
+int ofb_shot_host_jpeg(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p, int quality,
+                       uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms);
+/* The same with decoded BGR frames as input (gray conversion / resize on the GPU, as ofb_shot_bgr_host). */
+int ofb_shot_bgr_host_jpeg(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames, int W, int H, int dW, int dH, const ofb_params* p,
+                           int quality, uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms);
+/* The encoder on its own: n pictures (n, H, W, 3) uint8 BGR -> n JPEG streams, packed as above. */
+int ofb_jpeg_encode_host(ofb_context* ctx, const uint8_t* bgr, int n, int W, int H, int quality, uint8_t* jpeg, size_t jpeg_cap,
+                         uint32_t* jpeg_sizes);
 /* n_pairs INDEPENDENT pairs (prev[i], next[i]), each (H, W) uint8 tightly packed: the window loop of
  * optical_flow.py:83-99, whose pairs need not share frames.  Same outputs as ofb_shot_host. */
 int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, int n_pairs, int W, int H,
@@ -157,6 +172,8 @@ int ofb_stage_polyexp(ofb_context* ctx, const float* img, int W, int H, int poly
 int ofb_stage_update_matrices(ofb_context* ctx, const float* R0, const float* R1, const float* flow,
                               int W, int H, float* M);
 int ofb_stage_blur_solve(ofb_context* ctx, const float* M, int W, int H, int winsize, int gaussian, float* flow);
+/* quantised DCT coefficients of one picture in scan order: ceil(W/16)*ceil(H/16) MCUs x 6 blocks x 64 int16 (zigzag order) */
+int ofb_stage_jpeg_coefficients(ofb_context* ctx, const uint8_t* bgr, int W, int H, int quality, int16_t* coef);
 int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, int Hp, int W, int H,
                             double pyr_scale, float* flow);
 

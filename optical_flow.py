@@ -117,7 +117,7 @@ def write_mag_to_csv(f_path, mag, segment_timestamps):
 
 def main(features_root, frame_width, step_size, window_size, top_percentile, videoids, force_run):
     logger.info("Computing optical flow for {0} videos".format(len(videoids)))
-    engine = ofb.default_engine() if videoids else None
+    engine = None                     # created on the first video that needs work: an all-up-to-date run touches no GPU
     for videoid in tqdm(videoids):
         features_dir = os.path.join(features_root, videoid, EXTRACTOR)
         v_path = os.path.join(features_root, videoid, 'media', videoid + '.mp4')
@@ -129,6 +129,7 @@ def main(features_root, frame_width, step_size, window_size, top_percentile, vid
         if up_to_date and force_run != 'True':
             logger.info('optical flow was already done')
             continue
+        engine = engine or ofb.default_engine()
         segments, timestamps = get_optical_flow(v_path, frame_width, step_size, window_size, engine)
         write_mag_to_csv(f_path_csv, scale_magnitudes(segments, top_percentile), timestamps)
         if STANDALONE:

@@ -21,6 +21,7 @@
 // option "generic_kernels") runs the simple per-item global-memory kernels with identical results.
 #include "common.cuh"
 #include "launch.cuh"
+#include "jpeg.cuh"
 #include "../../include/optflow_b200.h"
 
 #include <algorithm>
@@ -102,6 +103,14 @@ struct ofb_context {
     bool use_hsv_table = true;          // option "hsv_table"
     float* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
+    // GPU JPEG encoder (jpeg.cu): workspaces for `jpeg_batch` pictures of jpeg_W x jpeg_H at jpeg_quality
+    JpegWork jw{};
+    int jpeg_W = 0, jpeg_H = 0, jpeg_quality = 0, jpeg_batch = 0;
+    std::vector<void*> jpeg_allocs;
+    uint8_t* jout[2] = {nullptr, nullptr};              // packed streams of a chunk, by chunk parity
+    unsigned long long* d_tot[2] = {nullptr, nullptr};  // {bytes of the chunk, overflow flag}
+    unsigned long long* h_tot = nullptr;                // pinned mirror, 2 x 2
+    cudaEvent_t ev_tot[2]{};
     // 8-bit bilinear resize tables of the last (source, destination) geometry (preprocess.cu)
     int rs_geom[4] = {0, 0, 0, 0};      // sW, sH, dW, dH
     int* rs_tab = nullptr;              // x0[dW] x1[dW] y0[dH] y1[dH] | short ax[2dW] ay[2dH]
@@ -139,6 +148,8 @@ struct DrainOnError {
         cudaGetLastError();
     }
 };
+
+struct JpegOut { uint8_t* out; size_t cap; uint32_t* sizes; int quality; };      // host destination of the JPEG delivery
 
 // ---- A.1 ------------------------------------------------------------------------------------
 int num_scales(int W, int H, double pyr_scale, int levels)
@@ -610,6 +621,53 @@ int bgr_geometry(ofb_context* ctx, int sW, int sH, int* dW, int* dH)
     return 0;
 }
 
+// ---- GPU JPEG encoder workspaces --------------------------------------------------------------------------------
+void free_jpeg(ofb_context* ctx)
+{
+    for (void* p : ctx->jpeg_allocs) cudaFree(p);
+    ctx->jpeg_allocs.clear();
+    ctx->jpeg_W = ctx->jpeg_H = ctx->jpeg_quality = ctx->jpeg_batch = 0;
+}
+
+int ensure_jpeg(ofb_context* ctx, int W, int H, int quality, int batch)
+{
+    if (W > 65535 || H > 65535) return fail(ctx, OFB_ERR_UNSUPPORTED, "JPEG pictures are limited to 65535 x 65535");
+    quality = std::max(1, std::min(quality, 100));
+    if (ctx->jpeg_W == W && ctx->jpeg_H == H && ctx->jpeg_quality == quality && ctx->jpeg_batch >= batch) return 0;
+    CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_d2h));
+    free_jpeg(ctx);
+    JpegWork& w = ctx->jw;
+    w.geom = jpeg_geometry(W, H);
+    const JpegGeom& g = w.geom;
+    const size_t B = (size_t)batch;
+    auto alloc = [&](void** out, size_t bytes) -> int {
+        void* p = nullptr;
+        CU(cudaMalloc(&p, bytes + 256));
+        ctx->jpeg_allocs.push_back(p);
+        *out = p;
+        return 0;
+    };
+    JpegTables host_tab;
+    jpeg_build_tables(W, H, quality, host_tab);
+    void* q;
+    if (int rc = alloc(&q, sizeof(JpegTables))) return rc;
+    CU(cudaMemcpy(q, &host_tab, sizeof(JpegTables), cudaMemcpyHostToDevice));
+    w.tables = (const JpegTables*)q; w.header_len = host_tab.header_len;
+    if (int rc = alloc((void**)&w.coef, B * g.nblk * 64 * sizeof(int16_t))) return rc;
+    if (int rc = alloc((void**)&w.blk_bits, B * g.nblk * sizeof(uint32_t))) return rc;
+    if (int rc = alloc((void**)&w.bits32, B * g.bits_cap + JPEG_SEG)) return rc;
+    if (int rc = alloc((void**)&w.total_bits, B * sizeof(uint32_t))) return rc;
+    if (int rc = alloc((void**)&w.seg_ff, B * g.nseg_cap * sizeof(uint32_t))) return rc;
+    if (int rc = alloc((void**)&w.out_off, B * sizeof(unsigned long long))) return rc;
+    for (int s = 0; s < 2; s++) {
+        if (int rc = alloc((void**)&ctx->jout[s], B * g.out_cap)) return rc;
+        if (int rc = alloc((void**)&ctx->d_tot[s], 2 * sizeof(unsigned long long))) return rc;
+    }
+    ctx->jpeg_W = W; ctx->jpeg_H = H; ctx->jpeg_quality = quality; ctx->jpeg_batch = batch;
+    return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -667,6 +725,8 @@ int ofb_create(int device, ofb_context** out)
     ok(cudaMalloc((void**)&c->sumacc, sizeof(double) * MAX_BATCH + 256));
     ok(cudaMalloc((void**)&c->sumout, sizeof(float) * MAX_BATCH + 256));
     ok(cudaMalloc((void**)&c->hsv_table, sizeof(unsigned) * 65536));
+    ok(cudaHostAlloc((void**)&c->h_tot, 4 * sizeof(unsigned long long), cudaHostAllocPortable));
+    for (int i = 0; i < 2; i++) ok(cudaEventCreateWithFlags(&c->ev_tot[i], cudaEventDisableTiming));
     if (rc != cudaSuccess) {
         std::string m = std::string("context setup: ") + cudaGetErrorString(rc);
         delete c;
@@ -692,6 +752,9 @@ void ofb_destroy(ofb_context* ctx)
     cudaDeviceSynchronize();
     ctx->prof.collect();
     free_plan(ctx->plan);
+    free_jpeg(ctx);
+    if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_tot[i]);
     for (int i = 0; i < 6; i++) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     if (ctx->rs_tab) cudaFree(ctx->rs_tab);
     cudaFree(ctx->minmax); cudaFree(ctx->sumacc); cudaFree(ctx->sumout); cudaFree(ctx->hsv_table);
@@ -940,9 +1003,10 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
 //   fptr != nullptr (shot only): frame i lives at fptr[i] (a decoder's own buffers; nothing is assembled on the host).
 static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next, int n_pairs, int W, int H, int sW, int sH,
                      const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, uint8_t* gray_out, float* device_ms,
-                     const uint8_t* const* fptr = nullptr)
+                     const uint8_t* const* fptr = nullptr, const JpegOut* jpg = nullptr)
 {
     if (fptr && !first) first = fptr[0];
+    const bool want_jpeg = jpg != nullptr;
     if (int rc = validate(ctx, W, H, OFB_U8, p)) return rc;
     const bool pairs = next != nullptr;
     if (!first || n_pairs < 1) return fail(ctx, OFB_ERR_BAD_ARG, pairs ? "need at least one pair" : "need at least two frames");
@@ -950,10 +1014,27 @@ static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next
     CU(cudaSetDevice(ctx->device));
     const int B = shot_batch(ctx, W, H, n_pairs);
     if (int rc = ensure_plan(ctx, W, H, OFB_U8, p, B)) return rc;
+    if (want_jpeg) if (int rc = ensure_jpeg(ctx, W, H, jpg->quality, B)) return rc;
     Plan& pl = ctx->plan;
     cudaStream_t sc = ctx->s_compute, su = ctx->s_h2d, sd = ctx->s_d2h;
     const size_t n = (size_t)W * H;
     const bool from_bgr = sW > 0;
+    uint32_t* d_jsizes = nullptr;
+    if (want_jpeg) { float* q; if (int rc = stage_buf(ctx, 5, sizeof(uint32_t) * (size_t)n_pairs, &q)) return rc; d_jsizes = (uint32_t*)q; }
+    size_t jpeg_done = 0;                                              // bytes of finished streams already queued for download
+    // JPEG streams of chunk c are packed in jout[c & 1]; their total size is only known on the device, so the download of
+    // chunk c is issued one iteration later, after a 16-byte read-back of the total (the GPU already runs chunk c+1 by then).
+    auto flush_jpeg = [&](int c) -> int {
+        const int par = c & 1;
+        CU(cudaEventSynchronize(ctx->ev_tot[par]));
+        const unsigned long long total = ctx->h_tot[2 * par], flag = ctx->h_tot[2 * par + 1];
+        if (flag) return fail(ctx, OFB_ERR_UNSUPPORTED, "a JPEG stream is larger than the raw picture (not a picture this encoder expects)");
+        if (jpeg_done + total > jpg->cap) return fail(ctx, OFB_ERR_BAD_ARG, "jpeg output buffer too small");
+        CU(cudaMemcpyAsync(jpg->out + jpeg_done, ctx->jout[par], (size_t)total, cudaMemcpyDeviceToHost, sd));
+        CU(cudaEventRecord(ctx->ev_out_free[par], sd));
+        jpeg_done += (size_t)total;
+        return 0;
+    };
     const size_t sn = from_bgr ? (size_t)sW * sH * 3 : n;                // bytes of one source frame
     float* d_sums = nullptr;
     if (magsum) if (int rc = stage_buf(ctx, 3, sizeof(float) * (size_t)n_pairs, &d_sums)) return rc;
@@ -1027,19 +1108,31 @@ static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next
         }
         CU(cudaEventRecord(ctx->ev_frame_free[par], sc));
         if (c >= 2) CU(cudaStreamWaitEvent(sc, ctx->ev_out_free[par], 0));
-        const bool mm = pairs ? solve_pairs(ctx, L, 0, b, pl.flow0[par], n, 2, bgr != nullptr)
-                              : solve_pairs(ctx, L, t0, b, pl.flow0[par], n, 1, bgr != nullptr);
-        if (bgr) picture(ctx, L, pl.flow0[par], n, n, pl.bgr[par], n * 3, b, mm);
+        const bool want_pic = bgr != nullptr || want_jpeg;
+        const bool mm = pairs ? solve_pairs(ctx, L, 0, b, pl.flow0[par], n, 2, want_pic)
+                              : solve_pairs(ctx, L, t0, b, pl.flow0[par], n, 1, want_pic);
+        if (want_pic) picture(ctx, L, pl.flow0[par], n, n, pl.bgr[par], n * 3, b, mm);
+        if (want_jpeg) launch_jpeg_encode(L, ctx->jw, pl.bgr[par], n * 3, b, ctx->jout[par], d_jsizes + t0, ctx->d_tot[par]);
         if (magsum) launch_sum_magnitude_batch(L, pl.flow0[par], n, n, ctx->sumacc, d_sums + t0, b);
         CU(cudaEventRecord(ctx->ev_out_ready[par], sc));
-        if (bgr || flow) {
+        if (bgr || flow || want_jpeg) {
             CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
             if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[par], (size_t)b * n * 3, cudaMemcpyDeviceToHost, sd));
             if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[par], (size_t)b * n * 8, cudaMemcpyDeviceToHost, sd));
-            CU(cudaEventRecord(ctx->ev_out_free[par], sd));
+            if (want_jpeg) {
+                CU(cudaMemcpyAsync(ctx->h_tot + 2 * par, ctx->d_tot[par], 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sd));
+                CU(cudaEventRecord(ctx->ev_tot[par], sd));
+                if (c >= 1) if (int rc = flush_jpeg(c - 1)) return rc;      // records ev_out_free of the previous chunk
+            } else {
+                CU(cudaEventRecord(ctx->ev_out_free[par], sd));
+            }
         } else {
             CU(cudaEventRecord(ctx->ev_out_free[par], sc));
         }
+    }
+    if (want_jpeg) {
+        if (int rc = flush_jpeg(n_chunks - 1)) return rc;
+        CU(cudaMemcpyAsync(jpg->sizes, d_jsizes, sizeof(uint32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, sd));
     }
     CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[(n_chunks - 1) & 1], 0));
     if (magsum) CU(cudaMemcpyAsync(magsum, d_sums, sizeof(float) * (size_t)n_pairs, cudaMemcpyDeviceToHost, sd));
@@ -1065,6 +1158,74 @@ int ofb_shot_host_v(ofb_context* ctx, const uint8_t* const* frames, int n_frames
     if (!frames) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer table");
     for (int i = 0; i < n_frames; i++) if (!frames[i]) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer");
     return host_impl(ctx, nullptr, nullptr, n_frames - 1, W, H, 0, 0, p, bgr, magsum, flow, nullptr, device_ms, frames);
+}
+
+int ofb_shot_host_jpeg(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p, int quality,
+                       uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms)
+{
+    if (!jpeg || !jpeg_sizes) return fail(ctx, OFB_ERR_BAD_ARG, "null jpeg output");
+    const JpegOut jo{jpeg, jpeg_cap, jpeg_sizes, quality};
+    return host_impl(ctx, frames, nullptr, n_frames - 1, W, H, 0, 0, p, nullptr, magsum, nullptr, nullptr, device_ms, nullptr, &jo);
+}
+
+int ofb_shot_bgr_host_jpeg(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames, int W, int H, int dW, int dH, const ofb_params* p,
+                           int quality, uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms)
+{
+    if (!ctx) return OFB_ERR_BAD_ARG;
+    if (!jpeg || !jpeg_sizes) return fail(ctx, OFB_ERR_BAD_ARG, "null jpeg output");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = bgr_geometry(ctx, W, H, &dW, &dH)) return rc;
+    const JpegOut jo{jpeg, jpeg_cap, jpeg_sizes, quality};
+    return host_impl(ctx, bgr_frames, nullptr, n_frames - 1, dW, dH, W, H, p, nullptr, magsum, nullptr, nullptr, device_ms, nullptr, &jo);
+}
+
+int ofb_jpeg_encode_host(ofb_context* ctx, const uint8_t* bgr, int n, int W, int H, int quality, uint8_t* jpeg, size_t jpeg_cap,
+                         uint32_t* jpeg_sizes)
+{
+    if (!ctx || !bgr || !jpeg || !jpeg_sizes || n < 1 || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t px = (size_t)W * H * 3;
+    const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, std::min<size_t>(64, (size_t)(256.0e6 / (double)px) + 1)));
+    if (int rc = ensure_jpeg(ctx, W, H, quality, B)) return rc;
+    float *dsrc, *dsz;
+    if (int rc = stage_buf(ctx, 0, px * B + 16, &dsrc)) return rc;
+    if (int rc = stage_buf(ctx, 1, sizeof(uint32_t) * (size_t)B, &dsz)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    Launch L = make_launch(ctx, s);
+    size_t done = 0;
+    for (int t0 = 0; t0 < n; t0 += B) {
+        const int b = std::min(B, n - t0);
+        CU(cudaMemcpyAsync(dsrc, bgr + (size_t)t0 * px, px * b, cudaMemcpyHostToDevice, s));
+        launch_jpeg_encode(L, ctx->jw, (const uint8_t*)dsrc, px, b, ctx->jout[0], (uint32_t*)dsz, ctx->d_tot[0]);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ctx->h_tot, ctx->d_tot[0], 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(jpeg_sizes + t0, dsz, sizeof(uint32_t) * (size_t)b, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (ctx->h_tot[1]) return fail(ctx, OFB_ERR_UNSUPPORTED, "a JPEG stream is larger than the raw picture");
+        if (done + ctx->h_tot[0] > jpeg_cap) return fail(ctx, OFB_ERR_BAD_ARG, "jpeg output buffer too small");
+        CU(cudaMemcpy(jpeg + done, ctx->jout[0], (size_t)ctx->h_tot[0], cudaMemcpyDeviceToHost));
+        done += (size_t)ctx->h_tot[0];
+    }
+    return OFB_OK;
+}
+
+int ofb_stage_jpeg_coefficients(ofb_context* ctx, const uint8_t* bgr, int W, int H, int quality, int16_t* coef)
+{
+    if (!ctx || !bgr || !coef || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_jpeg(ctx, W, H, quality, 1)) return rc;
+    const size_t px = (size_t)W * H * 3;
+    float *dsrc, *dsz;
+    if (int rc = stage_buf(ctx, 0, px + 16, &dsrc)) return rc;
+    if (int rc = stage_buf(ctx, 1, 64, &dsz)) return rc;
+    cudaStream_t s = ctx->s_compute;
+    Launch L = make_launch(ctx, s);
+    CU(cudaMemcpyAsync(dsrc, bgr, px, cudaMemcpyHostToDevice, s));
+    launch_jpeg_encode(L, ctx->jw, (const uint8_t*)dsrc, px, 1, ctx->jout[0], (uint32_t*)dsz, ctx->d_tot[0]);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(coef, ctx->jw.coef, sizeof(int16_t) * 64 * (size_t)ctx->jw.geom.nblk, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return OFB_OK;
 }
 
 int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, int n_pairs, int W, int H,

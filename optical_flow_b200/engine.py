@@ -246,6 +246,65 @@ class Farneback:
         self._check(self._L.ofb_shot_host_v(self._h, table, n, W, H, C.byref(prm), _ptr(bgr), _ptr(ms), _ptr(fl), C.byref(dev_ms)))
         return {"bgr": bgr, "magsum": ms, "flow": fl, "device_ms": float(dev_ms.value)}
 
+    def shot_jpeg(self, frames, quality=95, out=None, want_magsum=False, **params):
+        """`shot` whose pictures come back as the JPEG files the reference writes (visualize_optical_flow.py:57-58): the bytes of
+        cv2.imencode('.jpeg', picture) for every pair, encoded on the GPU.  Returns {"jpeg": uint8 buffer, "sizes", "offsets"};
+        stream i is jpeg[offsets[i]:offsets[i] + sizes[i]].  `out` may be a pre-allocated (pinned) uint8 buffer."""
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim != 3 or frames.dtype != np.uint8 or frames.shape[0] < 2:
+            raise ValueError("frames must be (n>=2, H, W) uint8")
+        n, H, W = frames.shape
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        if out is None:
+            out = np.empty((n - 1) * (W * H + 4096), np.uint8)         # 1 byte per pixel: ~10x a flow picture at quality 95
+        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        sizes = np.zeros(n - 1, np.uint32)
+        ms = np.zeros(n - 1, np.float32) if want_magsum else None
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_shot_host_jpeg(self._h, _ptr(frames), n, W, H, C.byref(prm), int(quality), _ptr(out), out.size,
+                                               _ptr(sizes), _ptr(ms), C.byref(dev_ms)))
+        offsets = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.int64)])
+        return {"jpeg": out, "sizes": sizes, "offsets": offsets, "magsum": ms, "device_ms": float(dev_ms.value)}
+
+    def shot_bgr_jpeg(self, frames_bgr, dsize=None, quality=95, **params):
+        """`shot_jpeg` fed with the decoded BGR frames (n, H, W, 3), as shot_bgr: what visualize_optical_flow.py's loop does
+        from `vid.read()` to `cv2.imwrite(flow_<ms>.jpeg)` (:23-58), with only the frames going up and the files coming back."""
+        f = self._bgr_stack(frames_bgr, "frames_bgr")
+        if f.shape[0] < 2:
+            raise ValueError("need at least two frames")
+        n, H, W = f.shape[:3]
+        dW, dH = (W, H) if dsize is None else (int(dsize[0]), int(dsize[1]))
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        out = np.empty((n - 1) * (dW * dH + 4096), np.uint8)
+        sizes = np.zeros(n - 1, np.uint32)
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_shot_bgr_host_jpeg(self._h, _ptr(f), n, W, H, 0 if dsize is None else dW, 0 if dsize is None else dH,
+                                                   C.byref(prm), int(quality), _ptr(out), out.size, _ptr(sizes), None, C.byref(dev_ms)))
+        offs = np.concatenate([[0], np.cumsum(sizes, dtype=np.int64)])
+        return {"files": [out[offs[i]:offs[i + 1]] for i in range(n - 1)], "sizes": sizes, "device_ms": float(dev_ms.value)}
+
+    def jpeg_encode(self, pictures, quality=95):
+        """cv2.imencode('.jpeg', picture)[1] for every (H, W, 3) uint8 BGR picture of `pictures` (n, H, W, 3), on the GPU.
+        Returns a list of uint8 arrays."""
+        pics = np.ascontiguousarray(pictures)
+        if pics.ndim == 3:
+            pics = pics[None]
+        if pics.ndim != 4 or pics.shape[3] != 3 or pics.dtype != np.uint8:
+            raise ValueError("pictures must be (n, H, W, 3) uint8")
+        n, H, W = pics.shape[:3]
+        out = np.empty(n * (W * H * 3 + 4096), np.uint8)
+        sizes = np.zeros(n, np.uint32)
+        self._check(self._L.ofb_jpeg_encode_host(self._h, _ptr(pics), n, W, H, int(quality), _ptr(out), out.size, _ptr(sizes)), "imencode")
+        offs = np.concatenate([[0], np.cumsum(sizes, dtype=np.int64)])
+        return [out[offs[i]:offs[i + 1]].copy() for i in range(n)]
+
+    def stage_jpeg_coefficients(self, picture, quality=95):
+        pic = np.ascontiguousarray(picture)
+        H, W = pic.shape[:2]
+        out = np.empty((((W + 15) // 16) * ((H + 15) // 16), 6, 64), np.int16)
+        self._check(self._L.ofb_stage_jpeg_coefficients(self._h, _ptr(pic), W, H, int(quality), _ptr(out)))
+        return out
+
     def pairs(self, prev_frames, next_frames, want_bgr=False, want_magsum=True, want_flow=False, **params):
         """n independent pairs (prev_frames[i], next_frames[i]) in one batched submission: the window loop of
         optical_flow.py:83-99 (its pairs need not share frames)."""

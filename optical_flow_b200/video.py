@@ -28,13 +28,19 @@ class FrameReader:
         """(ok, frame) exactly as `vid.set(cv2.CAP_PROP_POS_FRAMES, pos); vid.read()` returns them."""
         target = int(pos)
         ahead = None if self._next is None else target - self._next
-        if ahead is not None and 0 <= ahead <= self.max_forward:
+        forward = ahead is not None and 0 <= ahead <= self.max_forward
+        if forward:
             for _ in range(ahead):
                 self.grabs += 1
                 if not self.vid.grab():
                     self._next = None
                     return False, None
-        else:
+            # cv2 resolves a seek from the stream's timestamps (dts_to_frame_number); on VFR / drop-frame streams counting grabs
+            # can land elsewhere.  The decoder reports the index of the frame it will return next: if that is not the
+            # target, do what the reference does.
+            if int(self.vid.get(cv2.CAP_PROP_POS_FRAMES)) != target:
+                forward = False
+        if not forward:
             self.seeks += 1
             self.vid.set(cv2.CAP_PROP_POS_FRAMES, pos)
         ok, frame = self.vid.read()

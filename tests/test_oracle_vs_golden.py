@@ -127,3 +127,35 @@ def test_preprocess_oracle_fuzz_against_installed_cv2(oracle):
         assert np.array_equal(oracle.resize_u8(src, (dw, dh)), cv2.resize(src, (dw, dh))), (sw, sh, dw, dh, cn)
         if cn == 3:
             assert np.array_equal(oracle.bgr2gray(src), cv2.cvtColor(src, cv2.COLOR_BGR2GRAY))
+
+
+# ---- the JPEG artefact (visualize_optical_flow.py:57-58): oracle/jpeg_oracle.c against cv2.imencode's bytes ----------------
+def _jpeg_cases():
+    import os
+    z = np.load(os.path.join(GOLDEN_DIR, "jpeg_cases.npz"))
+    return z, sorted(k[:-4] for k in z.files if k.endswith("_img"))
+
+
+@pytest.mark.parametrize("name", _jpeg_cases()[1])
+def test_jpeg_oracle_reproduces_cv2_imencode_byte_for_byte(oracle, name):
+    z, _ = _jpeg_cases()
+    img, ref, q = z[name + "_img"], z[name + "_jpg"], int(z[name + "_q"])
+    got = oracle.jpeg_encode(img, q)
+    assert got.size == ref.size and np.array_equal(got, ref), (name, got.size, ref.size)
+    hdr = oracle.jpeg_header(img.shape[1], img.shape[0], q)
+    assert np.array_equal(hdr, ref[:hdr.size])
+
+
+def test_jpeg_oracle_against_the_installed_cv2_on_fresh_pictures(oracle):
+    """When cv2 is importable (it is in this image), fuzz the oracle against it beyond the committed fixtures."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    for i in range(12):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 90))
+        q = int(rng.choice([95, 95, 30, 75, 100]))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if i % 3 == 0:                                        # smooth content: long zero runs, ZRL codes
+            img = (np.add.outer(np.arange(h) * 3, np.arange(w) * 2)[..., None] % 256 + np.array([0, 40, 90])).astype(np.uint8)
+        ref = cv2.imencode(".jpeg", img, [cv2.IMWRITE_JPEG_QUALITY, q])[1].ravel()
+        got = oracle.jpeg_encode(img, q)
+        assert np.array_equal(got, ref), (h, w, q)

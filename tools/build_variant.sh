@@ -6,7 +6,7 @@ cd "$(dirname "$0")/../optical_flow_b200/csrc"
 name=$1; unit=$2; shift 2
 make -s
 objs=""
-for f in pyramid polyexp matrices blur_solve iter viz preprocess engine; do
+for f in pyramid polyexp matrices blur_solve iter viz preprocess jpeg engine; do
   if [ "$f.cu" = "$unit" ]; then
     nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false -Xcompiler -fPIC \
          -Xcompiler -fvisibility=hidden "$@" -c $f.cu -o ../../build/obj/${f}_$name.o

@@ -10,10 +10,11 @@ and `source_<ms>.jpeg` (the frame itself), sampling every 300 ms between shot_be
 What differs is only WHERE the hot path runs: the reference calls cvtColor(BGR2GRAY) + cv2.calcOpticalFlowFarneback +
 cartToPolar + normalize + cvtColor once per pair in a Python loop (:31-55); here the sampled BGR frames of the shot are
 handed to the GPU engine as ONE shot (optical_flow_b200.Farneback.shot_bgr -> C-ABI ofb_shot_bgr_host), which converts
-to gray on the device, expands each frame once, batches the pairs, and returns the BGR pictures.  Decoding
-(cv2.VideoCapture) and JPEG encoding stay with cv2 on the host, as in the reference; frames ahead of the decoder are
-reached by decoding forward instead of a seek per frame, and the JPEGs are encoded by a small thread pool
-(optical_flow_b200/video.py).
+to gray on the device, expands each frame once, batches the pairs, encodes every flow picture as the baseline JPEG
+cv2.imwrite would produce (same bytes: optical_flow_b200/csrc/jpeg.cu) and returns the FILES -- ~0.2 MB per 1080p pair
+cross PCIe instead of a 6.2 MB raw picture.  Decoding (cv2.VideoCapture) and the JPEG of the source frame stay with cv2 on
+the host, as in the reference; frames ahead of the decoder are reached by decoding forward instead of a seek per frame,
+and the source JPEGs are encoded by a small thread pool (optical_flow_b200/video.py).
 """
 import argparse
 import os
@@ -64,10 +65,14 @@ def get_optical_flow(v_path, images_path, start_ms, end_ms, engine=None):
     written = []
     frames_q = queue.Queue(maxsize=2 * MAX_FRAMES)
 
+    failure = []
+
     def decode():
         try:
             for item in sample_shot(v_path, start_ms, end_ms):
                 frames_q.put(item)
+        except BaseException as e:          # re-raised in the caller's thread: the reference would have crashed here too
+            failure.append(e)
         finally:
             frames_q.put(None)
 
@@ -81,15 +86,18 @@ def get_optical_flow(v_path, images_path, start_ms, end_ms, engine=None):
             else:
                 positions.append(item[0]); chunk.append(item[1]); fps = item[2]
             if len(chunk) >= 2 and (done or len(chunk) == MAX_FRAMES):
-                pictures = eng.shot_bgr(np.stack(chunk), want_bgr=True, **ofb.REFERENCE_PARAMS)["bgr"]    # hot path
+                files = eng.shot_bgr_jpeg(np.stack(chunk), **ofb.REFERENCE_PARAMS)["files"]    # hot path, :31-58
                 for k in range(1, len(chunk)):
                     stamp = str(int(positions[k] / fps * 1000))
                     path_flow = os.path.join(images_path, "flow_" + stamp + ".jpeg")
                     path_source = os.path.join(images_path, "source_" + stamp + ".jpeg")
-                    out.imwrite(path_flow, pictures[k - 1])
+                    with open(path_flow, "wb") as fh:          # the bytes cv2.imwrite(path_flow, picture) would write
+                        fh.write(files[k - 1].tobytes())
                     out.imwrite(path_source, chunk[k])
                     written += [path_flow, path_source]
                 chunk, positions = chunk[-1:], positions[-1:]
+    if failure:
+        raise failure[0]
     return written
 
 
