@@ -572,6 +572,13 @@ def run_feature(args, rank, local_rank, world):
     launches = sum(v[0] for v in eng.kernel_stats().values())
     t_ev, t_wall = dist.reduce_max(ms), dist.reduce_max(wall)
     total = dist.reduce_sum(P * args.steps)
+    kernels = {}
+    if rank == 0:                                       # one extra pass with CUDA events around every launch
+        eng.set_option("profile", 1)
+        eng.reset_kernel_stats()
+        eng.pairs(prev, nxt, want_magsum=True, **PARAMS)
+        kernels = {k: {"launches": c, "total_ms": round(t, 3)} for k, (c, t) in sorted(eng.kernel_stats().items(), key=lambda kv: -kv[1][1]) if t > 0}
+        eng.set_option("profile", 0)
     if rank == 0:
         peak, peak_src = peaks()
         alg = ofb.algorithmic_bytes(W, H, with_viz=False, **PARAMS) + 8.0 * W * H
@@ -587,7 +594,7 @@ def run_feature(args, rank, local_rank, world):
                           "gpu_launches": int(launches),
                           "roofline_pipeline": {"alg_bytes_per_pair": alg, "achieved": v / world * alg / 1e9, "peak": peak,
                                                 "frac": v / world * alg / 1e9 / peak, "unit": "GB/s", "peak_source": peak_src},
-                          "magsum_first": float(r["magsum"][0])}), flush=True)
+                          "kernels": kernels, "magsum_first": float(r["magsum"][0])}), flush=True)
     dist.barrier()
 
 

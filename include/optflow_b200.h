@@ -190,6 +190,9 @@ int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, in
  *                      (cp.async.bulk.tensor + mbarrier, double-buffered); bit-identical results, measured slower
  *                      than the default one-tile-per-CTA kernel on B200, so off by default */
 int ofb_set_option(ofb_context* ctx, const char* name, int value);
+/* Every workspace of the current plan carries a 256-byte guard band on both sides: returns how many guard bytes have been
+ * overwritten since the plan was built (0 = no out-of-bounds write next to a buffer), or a negative status. */
+int ofb_debug_check_guards(ofb_context* ctx);
 
 typedef struct ofb_kernel_stat {
     char name[48];

@@ -68,6 +68,7 @@ struct IterArgs {
     SlotRing R; int slot0;
     float2* flow; size_t flow_item;
     int W, H, strip_rows; float c;          // c = 1e-3 * winsize^4
+    double c64;                             // the same in f64 (k_iter64)
     int prefetch;                           // 1 = software-prefetch the next step's lines into L2
     int reverse;                            // 1 = walk the grid backwards: the tiles the previous launch wrote last (still in L2) are read first
     unsigned* minmax;                       // non-null (FUSE = false only): fold min / max of |flow| of item z into minmax[2z..]
@@ -144,6 +145,17 @@ void launch_pyr_v(Launch& L, const float* T, int H, int t_pitch, const float* ta
                   float* I, int Wk, int Hk, int i_pitch);
 
 void launch_pyr2(Launch& L, int dtype, const PyrArgs& a, int batch);
+// scales 1..nlev (<= 3) of a batch of u8 frames in one pass over each frame (pyr_scale 0.5, sizes multiple of 8)
+struct PyrFusedLaunch {
+    const void* src; size_t src_item, src_pitch;
+    int W, H, nlev;
+    int Wk[3], Hk[3], pitch[3];
+    const int* sx[3]; const float* ax[3]; const int* sy[3]; const float* ay[3];
+    float* I[3]; size_t i_item[3];
+    const float* taps[3];               // host pointers: 3, 9 and 19 taps
+};
+bool pyr_fused_supported(int dtype, int W, int H, double pyr_scale, const void* src, size_t src_pitch, size_t src_item);
+void launch_pyr_fused(Launch& L, const PyrFusedLaunch& f, int batch);
 
 // polyexp.cu -- A.5/A.6
 struct PolyConst { const float* g; const float* xg; const float* xxg; int n; double ig11, ig03, ig33, ig55; };

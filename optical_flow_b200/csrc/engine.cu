@@ -62,6 +62,8 @@ struct Plan {
     int K = 0;
     float* T = nullptr; size_t t_item = 0;      // batch x (H x pitch_1): row-pass intermediate of the pyramid
     float* I = nullptr; size_t i_item = 0;      // batch x level image
+    float* If[3] = {nullptr, nullptr, nullptr}; // batch x level image of scales 1..3 (one-pass pyramid)
+    bool pyr_fused = false;                     // geometry allows k_pyr_fused (pyr_scale 0.5, sizes multiple of 8)
     float* tmp3 = nullptr;              // 3 planes (generic polyexp, one item)
     float* M[2] = {nullptr, nullptr};   // batch x 5 planes, ping-pong
     size_t m_item = 0;
@@ -77,6 +79,7 @@ struct Plan {
     float* sums = nullptr;              // per-pair magnitude sums of a shot (host API), grown on demand
     size_t sums_cap = 0;
     std::vector<void*> allocs;
+    std::vector<std::pair<unsigned char*, size_t>> guards;     // (allocation base, payload bytes) of every guarded workspace
     bool fast_poly = false, fast_iter = false;
     std::vector<float> gk;              // host copy of the Gaussian window half taps
 };
@@ -107,6 +110,7 @@ struct ofb_context {
     JpegWork jw{};
     int jpeg_W = 0, jpeg_H = 0, jpeg_quality = 0, jpeg_batch = 0;
     std::vector<void*> jpeg_allocs;
+    std::vector<std::pair<unsigned char*, size_t>> jpeg_guards;
     uint8_t* jout[2] = {nullptr, nullptr};              // packed streams of a chunk, by chunk parity
     unsigned long long* d_tot[2] = {nullptr, nullptr};  // {bytes of the chunk, overflow flag}
     unsigned long long* h_tot = nullptr;                // pinned mirror, 2 x 2
@@ -265,11 +269,29 @@ void free_plan(Plan& pl)
     pl = Plan();
 }
 
+// Every workspace is allocated with a 256-byte guard band in front and behind, filled with GUARD_BYTE; ofb_debug_check_guards
+// counts the guard bytes that no longer hold it.  compute-sanitizer is not available on the B200 pool this was developed on,
+// so this (plus the bitwise repeat / batch / shard invariance tests) is how out-of-bounds WRITES next to a buffer are caught.
+constexpr size_t GUARD = 256;
+constexpr int GUARD_BYTE = 0xA5;
+
+int guarded_alloc(ofb_context* ctx, std::vector<void*>& owner, std::vector<std::pair<unsigned char*, size_t>>& guards, void** out, size_t bytes)
+{
+    unsigned char* p = nullptr;
+    bytes = (bytes + 255) & ~(size_t)255;
+    CU(cudaMalloc((void**)&p, bytes + 2 * GUARD));
+    CU(cudaMemset(p, GUARD_BYTE, GUARD));
+    CU(cudaMemset(p + GUARD + bytes, GUARD_BYTE, GUARD));
+    owner.push_back(p);
+    guards.push_back({p, bytes});
+    *out = p + GUARD;
+    return 0;
+}
+
 template <class T> int dalloc(ofb_context* ctx, Plan& pl, T** out, size_t count)
 {
     void* p = nullptr;
-    CU(cudaMalloc(&p, count * sizeof(T) + 256));
-    pl.allocs.push_back(p);
+    if (int rc = guarded_alloc(ctx, pl.allocs, pl.guards, &p, count * sizeof(T) + 256)) return rc;
     *out = (T*)p;
     return 0;
 }
@@ -373,6 +395,14 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
         if (int rc = dalloc(ctx, pl, &pl.flow0[s], B * n)) return rc;
         if (int rc = dalloc(ctx, pl, &pl.bgr[s], B * n * 3)) return rc;
     }
+    pl.pyr_fused = dtype == OFB_U8 && p->pyr_scale == 0.5 && W % 8 == 0 && H % 8 == 0 && W >= 64 && H >= 64 && pl.K >= 1;
+    for (int k = 1; k <= std::min(pl.K, 3) && pl.pyr_fused; k++) {
+        static const int want_ks[4] = {0, 3, 9, 19};
+        if (pl.lv[k].ksize != want_ks[k]) { pl.pyr_fused = false; break; }
+    }
+    if (pl.pyr_fused)
+        for (int k = 1; k <= std::min(pl.K, 3); k++)
+            if (int rc = dalloc(ctx, pl, &pl.If[k - 1], B * pl.lv[k].plane())) return rc;
     pl.fast_poly = polyexp2_supported(p->poly_n);
     pl.fast_iter = iter_supported(p->winsize) && p->iterations >= 1;
     pl.gk = gk;
@@ -398,9 +428,30 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
 {
     Plan& pl = ctx->plan;
     const bool fast = pl.fast_poly && !ctx->generic;
+    // scales 1..3 in one pass over the frames when the geometry allows it (pyramid.cu k_pyr_fused)
+    int nfused = 0;
+    if (fast && pl.pyr_fused && ctx->kopt.pyr_fused && pyr_fused_supported(pl.dtype, pl.W, pl.H, pl.p.pyr_scale, d_frames, pitch_bytes, item_bytes)) {
+        nfused = std::min(pl.K, 3);
+        PyrFusedLaunch f{};
+        f.src = d_frames; f.src_item = item_bytes; f.src_pitch = pitch_bytes; f.W = pl.W; f.H = pl.H; f.nlev = nfused;
+        for (int k = 1; k <= nfused; k++) {
+            const Level& l = pl.lv[k];
+            f.Wk[k - 1] = l.W; f.Hk[k - 1] = l.H; f.pitch[k - 1] = l.pitch;
+            f.sx[k - 1] = l.sx; f.ax[k - 1] = l.ax; f.sy[k - 1] = l.sy; f.ay[k - 1] = l.ay;
+            f.I[k - 1] = pl.If[k - 1]; f.i_item[k - 1] = l.plane(); f.taps[k - 1] = l.taps_h.data();
+        }
+        launch_pyr_fused(L, f, count);
+    }
     for (int k = pl.K; k >= 0; k--) {
         Level& l = pl.lv[k];
         const int slot0 = f0 % pl.nslots;
+        if (fast && k >= 1 && k <= nfused) {
+            PolyArgs a = pl.pa;
+            a.src = pl.If[k - 1]; a.src_item = l.plane() * sizeof(float); a.src_pitch = (size_t)l.pitch * sizeof(float);
+            a.W = l.W; a.H = l.H; a.R = ring(pl, l, slot_step); a.slot0 = slot0;
+            launch_polyexp2(L, 0, a, count);
+            continue;
+        }
         if (fast && k == 0) {
             PolyArgs a = pl.pa;
             a.src = d_frames; a.src_item = item_bytes; a.src_pitch = pitch_bytes;
@@ -481,6 +532,7 @@ bool solve_pairs(ofb_context* ctx, Launch& L, int t0, int count, float2* d_flow,
                     a.R = ring(pl, l, step); a.slot0 = (slot0 + z0 * step) % pl.nslots;
                     a.flow = flow + (size_t)z0 * fitem; a.flow_item = fitem;
                     a.W = l.W; a.H = l.H; a.c = gaussian ? 1e-3f : c4;
+                    a.c64 = 1e-3 * (double)p.winsize * p.winsize * p.winsize * p.winsize;
                     a.gauss = gaussian ? 1 : 0;
                     if (gaussian) for (size_t q = 0; q < pl.gk.size() && q < 17; q++) a.gk[q] = pl.gk[q];
                     a.minmax = (fold_minmax && last && k == 0) ? ctx->minmax + 2 * z0 : nullptr;
@@ -626,6 +678,7 @@ void free_jpeg(ofb_context* ctx)
 {
     for (void* p : ctx->jpeg_allocs) cudaFree(p);
     ctx->jpeg_allocs.clear();
+    ctx->jpeg_guards.clear();
     ctx->jpeg_W = ctx->jpeg_H = ctx->jpeg_quality = ctx->jpeg_batch = 0;
 }
 
@@ -641,13 +694,7 @@ int ensure_jpeg(ofb_context* ctx, int W, int H, int quality, int batch)
     w.geom = jpeg_geometry(W, H);
     const JpegGeom& g = w.geom;
     const size_t B = (size_t)batch;
-    auto alloc = [&](void** out, size_t bytes) -> int {
-        void* p = nullptr;
-        CU(cudaMalloc(&p, bytes + 256));
-        ctx->jpeg_allocs.push_back(p);
-        *out = p;
-        return 0;
-    };
+    auto alloc = [&](void** out, size_t bytes) -> int { return guarded_alloc(ctx, ctx->jpeg_allocs, ctx->jpeg_guards, out, bytes + 256); };
     JpegTables host_tab;
     jpeg_build_tables(W, H, quality, host_tab);
     void* q;
@@ -1454,6 +1501,7 @@ int ofb_stage_blur_solve(ofb_context* ctx, const float* M, int W, int H, int win
         a.Min = dM; a.Mout = nullptr; a.m_item = 0; a.plane = plane; a.pitch = pitch;
         a.flow = (float2*)dfl; a.flow_item = 0; a.W = W; a.H = H;
         a.c = gaussian ? 1e-3f : (float)(1e-3 * (double)winsize * winsize * winsize * winsize);
+        a.c64 = 1e-3 * (double)winsize * winsize * winsize * winsize;
         a.gauss = gaussian ? 1 : 0;
         if (gaussian) for (size_t q = 0; q < gk.size() && q < 17; q++) a.gk[q] = gk[q];
         launch_iter(L, a, winsize, false, 1);
@@ -1486,6 +1534,26 @@ int ofb_stage_upsample_flow(ofb_context* ctx, const float* prev_flow, int Wp, in
 }
 
 // ---- options and measurement -----------------------------------------------------------------------
+int ofb_debug_check_guards(ofb_context* ctx)
+{
+    if (!ctx) return OFB_ERR_BAD_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<unsigned char> h(2 * GUARD);
+    int bad = 0;
+    auto scan = [&](const std::vector<std::pair<unsigned char*, size_t>>& gs) -> int {
+        for (const auto& g : gs) {
+            CU(cudaMemcpy(h.data(), g.first, GUARD, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(h.data() + GUARD, g.first + GUARD + g.second, GUARD, cudaMemcpyDeviceToHost));
+            for (unsigned char b : h) bad += b != GUARD_BYTE;
+        }
+        return 0;
+    };
+    if (int rc = scan(ctx->plan.guards)) return rc;
+    if (int rc = scan(ctx->jpeg_guards)) return rc;
+    return bad;
+}
+
 int ofb_set_option(ofb_context* ctx, const char* name, int value)
 {
     if (!ctx || !name) return OFB_ERR_BAD_ARG;
@@ -1494,6 +1562,9 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!strcmp(name, "iter_ilp")) { ctx->kopt.iter_ilp = value; return OFB_OK; }
     if (!strcmp(name, "iter_prefetch")) { ctx->kopt.iter_prefetch = value; return OFB_OK; }
     if (!strcmp(name, "polyexp_tma")) { ctx->kopt.polyexp_tma = value; return OFB_OK; }
+    if (!strcmp(name, "pyr_fused")) { ctx->kopt.pyr_fused = value; return OFB_OK; }
+    if (!strcmp(name, "polyexp_fast")) { ctx->kopt.polyexp_fast = value; return OFB_OK; }
+    if (!strcmp(name, "f32_window_sums")) { ctx->kopt.f32_window_sums = value; return OFB_OK; }
     if (!strcmp(name, "hsv_table")) { ctx->use_hsv_table = value != 0; return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }

@@ -370,6 +370,208 @@ static void run_iter(Launch& L, IterArgs a, int batch)
     });
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_iter64<M, FUSE>: the box-window iteration with the window sums and the 2x2 solve in FP64, as cv2 has them
+// (FarnebackUpdateFlow_Blur keeps double running sums and a double solve).
+//
+// Why not f32: where the 15x15 neighbourhood holds a single edge direction the matrix [g11 g12; g12 g22] is rank-deficient
+// and det = g11*g22 - g12^2 cancels; a 1e-7 relative error in the SUMS (not in the solve) then moves the flow by
+// cond * 1e-7, and on clean edges cond reaches 1e5..1e7: the f32 van Herk sums of k_iter were up to 0.2 px (checkerboard)
+// and 0.9 px (perpendicular step edges) away from cv2 while cv2 and the f64 oracle agreed to 4e-3 / 2e-6
+// (profiles/r2c_benchpath_adversarial_f32sums.log).  Textured frames never showed it.
+//
+// Same strip walk as k_iter.  V phase: thread = (channel, column) keeps the last R = 2M+1 raw f32 values of its column in
+// registers and ONE running f64 window sum (cv2's own scheme; restarted at every strip), 2 DADD + 2 F2F per element.
+// H phase: thread = (channel, row, segment), van Herk in f64 out of shared memory.  S phase: thread = pixel, determinant and
+// numerators with DFMA, rounded to f32 only for the final quotient, then (FUSE) UpdateMatrices exactly as in k_iter.
+// Shared memory: 8 * 5R * (97 + TW + 1) bytes = 108 KB for winsize 15, two CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+template <int M, bool FUSE>
+__global__ void __launch_bounds__(IT_THREADS, (M <= 7) ? 2 : 1)
+k_iter64(IterArgs a)
+{
+    constexpr int R = 2 * M + 1;
+    constexpr int TW = IT_CW - 2 * M;
+    constexpr int HP = TW + 1;
+    constexpr int NSEG = (TW + R - 1) / R;
+    static_assert(TW >= 1 && 5 * R * NSEG <= IT_THREADS, "H phase: one thread per (channel, row, segment)");
+    extern __shared__ double it_smem64[];
+    double* sV = it_smem64;                     // 5 * R * IT_VP
+    double* sH = it_smem64 + 5 * R * IT_VP;     // 5 * R * HP
+
+    const int tid = threadIdx.x;
+    const int z = blockIdx.x, bx = blockIdx.y, bs = blockIdx.z;
+    const int W = a.W, H = a.H;
+    const int x0 = bx * TW;
+    const int ybeg = bs * a.strip_rows;
+    const int yend = min(ybeg + a.strip_rows, H);
+    if (ybeg >= H) return;
+
+    const int vc = tid / IT_CW, vcol = tid - vc * IT_CW;
+    const int gx = min(max(x0 - M + vcol, 0), W - 1);                 // replicate border in x
+    const float* __restrict__ src = a.Min + (size_t)z * a.m_item + (size_t)vc * a.plane + gx;
+    const int pitch = a.pitch;
+
+    float win[R];                                                      // rows y-M .. y+M of this column, raw
+    double S = 0.0;                                                    // their sum
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        win[i] = src[(size_t)min(max(ybeg - M + i, 0), H - 1) * pitch];
+        S += (double)win[i];
+    }
+
+    RView R0{nullptr, nullptr, 0}, R1{nullptr, nullptr, 0};
+    float* mout = nullptr;
+    float2* fout = nullptr;
+    if (FUSE) {
+        const int s0 = a.R.first(a.slot0, z), s1 = a.R.wrap(s0 + 1);
+        R0 = a.R.slot(s0); R1 = a.R.slot(s1);
+        mout = a.Mout + (size_t)z * a.m_item;
+    } else {
+        fout = a.flow + (size_t)z * a.flow_item;
+    }
+    const double c64 = a.c64;
+    float mag_lo = __int_as_float(0x7f800000), mag_hi = 0.f;
+
+    for (int ys = ybeg; ys < yend; ys += R) {
+        // ---- V phase ----
+        float nb[R];                                                   // rows ys+M+1 .. ys+3M+1 enter the window during this step
+        if (ys + 3 * M + 1 < H) {
+            const float* pb = src + (size_t)(ys + M + 1) * pitch;
+#pragma unroll
+            for (int r = 0; r < R; r++) nb[r] = pb[r * pitch];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) nb[r] = src[(size_t)min(ys + M + 1 + r, H - 1) * pitch];
+        }
+        if (a.prefetch && ys + R < yend) {
+            const int yn = ys + R;
+            if (tid < 5 * R * 4) {
+                const int c = tid / (R * 4), rem = tid - c * (R * 4), r = rem >> 2, l = rem & 3;
+                const int row = min(yn + M + 1 + r, H - 1);
+                const int col = max(x0 - M, 0) + 32 * l;
+                if (col < pitch) {
+                    const float* p = a.Min + (size_t)z * a.m_item + (size_t)c * a.plane + (size_t)row * pitch + col;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
+            }
+            if (FUSE) {
+                constexpr int LA = (TW * 16 + 127) / 128 + 1;
+                if (tid < R * LA) {
+                    const int r = tid / LA, l = tid - r * LA;
+                    const int row = min(yn + r, H - 1), col = x0 + 8 * l;
+                    if (col < pitch) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R0.a + (size_t)row * pitch + col));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R1.a + (size_t)row * pitch + col));
+                    }
+                } else if (tid < R * LA + R * 4) {
+                    const int j = tid - R * LA, r = j >> 2, l = j & 3;
+                    const int row = min(yn + r, H - 1), col = x0 + 32 * l;
+                    if (col < pitch) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R0.b + (size_t)row * pitch + col));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(R1.b + (size_t)row * pitch + col));
+                    }
+                }
+            }
+        }
+        {
+            double* v = sV + vc * R * IT_VP + vcol;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                v[r * IT_VP] = S;                                      // window of row ys + r
+                S = (S + (double)nb[r]) - (double)win[r];              // slide down one row
+                win[r] = nb[r];
+            }
+        }
+        __syncthreads();
+
+        // ---- H phase: item = (channel*R + row, segment), van Herk along x in f64 ----
+        if (tid < 5 * R * NSEG) {
+            const int seg = tid / (5 * R), rc = tid - seg * (5 * R);
+            const int xa = seg * R;
+            const double* v = sV + rc * IT_VP + xa;
+            double* h = sH + rc * HP + xa;
+            double sa[R];
+#pragma unroll
+            for (int i = 0; i < R; i++) sa[i] = (xa + i < IT_CW) ? v[i] : 0.0;
+#pragma unroll
+            for (int i = R - 2; i >= 0; i--) sa[i] = sa[i] + sa[i + 1];
+            if (xa < TW) h[0] = sa[0];
+            double p = 0.0;
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                if (xa + r < TW) {
+                    const double q = v[R + r - 1];                     // column xa+r+2M <= CW-1
+                    p = (r == 1) ? q : p + q;
+                    h[r] = sa[r] + p;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- S phase: item = pixel ----
+        for (int i = tid; i < R * TW; i += IT_THREADS) {
+            const int r = i / TW, lx = i - r * TW;
+            const int y = ys + r, x = x0 + lx;
+            if (y < yend && x < W) {
+                const double* h = sH + r * HP + lx;
+                const double g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
+                // cv2: idet = 1 / (g11*g22 - g12^2 + 1e-3) on sums scaled by 1/w^2; here unscaled sums, c64 = 1e-3 * w^4
+                const double det = fma(g11, g22, -(g12 * g12)) + c64;
+                const double nx = fma(g11, h2, -(g12 * h1));
+                const double ny = fma(g22, h1, -(g12 * h2));
+                const float idet = __frcp_rn((float)det);
+                const float fx = __fmul_rn((float)nx, idet);
+                const float fy = __fmul_rn((float)ny, idet);
+                if (FUSE) {
+                    M5 m = um_pixel(x, y, fx, fy, R0, R1, W, H);
+                    float* o = mout + (size_t)y * pitch + x;
+#pragma unroll
+                    for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
+                } else {
+                    fout[(size_t)y * W + x] = make_float2(fx, fy);
+                    if (a.minmax) {
+                        const float mg = sqrtf(fmaf(fx, fx, fy * fy));
+                        mag_lo = fminf(mag_lo, mg); mag_hi = fmaxf(mag_hi, mg);
+                    }
+                }
+            }
+        }
+        // no barrier here: the next V phase writes only sV (last read before the barrier above); sH is next written after
+        // the barrier that follows that V phase.
+    }
+    if (!FUSE && a.minmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mag_lo = fminf(mag_lo, __shfl_xor_sync(0xffffffffu, mag_lo, o));
+            mag_hi = fmaxf(mag_hi, __shfl_xor_sync(0xffffffffu, mag_hi, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(a.minmax + 2 * z, __float_as_uint(mag_lo));
+            atomicMax(a.minmax + 2 * z + 1, __float_as_uint(mag_hi));
+        }
+    }
+}
+
+template <int M, bool FUSE>
+static void run_iter64(Launch& L, IterArgs a, int batch)
+{
+    constexpr int R = 2 * M + 1, TW = IT_CW - 2 * M, HP = TW + 1;
+    const size_t smem = sizeof(double) * (5 * R * IT_VP + 5 * R * HP);
+    static unsigned long long configured = 0;
+    L.dyn_smem(k_iter64<M, FUSE>, smem, configured);
+    const int xt = divup(a.W, TW);
+    int want = std::max(1, (L.sm_count + xt - 1) / xt);      // same strip partition rule as run_iter (results must not depend on the batch)
+    int strip = divup(divup(a.H, want), R) * R;
+    strip = std::max(strip, std::min(a.H, 4 * R));
+    strip = divup(strip, R) * R;
+    a.strip_rows = strip;
+    a.prefetch = L.opt.iter_prefetch;
+    dim3 grid(batch, xt, divup(a.H, strip));
+    L.run(FUSE ? "iter_fused" : "iter_last", [&](cudaStream_t s) { k_iter64<M, FUSE><<<grid, IT_THREADS, smem, s>>>(a); });
+}
+
 bool iter_supported(int winsize) { int m = winsize / 2; return m >= 1 && m <= 16; }
 
 
@@ -382,6 +584,19 @@ void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int ba
     case MM:                                                                                  \
         if (!fuse_um) run_iter<MM, false, 1, true>(L, a, batch);                    \
         else run_iter<MM, true, 1, true>(L, a, batch);                              \
+        return;
+            OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
+            OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)
+#undef OFB_CASE
+            default: return;
+        }
+    }
+    if (!L.opt.f32_window_sums) {
+        switch (m) {
+#define OFB_CASE(MM)                                                                          \
+    case MM:                                                                                  \
+        if (!fuse_um) run_iter64<MM, false>(L, a, batch);                                     \
+        else run_iter64<MM, true>(L, a, batch);                                               \
         return;
             OFB_CASE(1) OFB_CASE(2) OFB_CASE(3) OFB_CASE(4) OFB_CASE(5) OFB_CASE(6) OFB_CASE(7) OFB_CASE(8)
             OFB_CASE(9) OFB_CASE(10) OFB_CASE(11) OFB_CASE(12) OFB_CASE(13) OFB_CASE(14) OFB_CASE(15) OFB_CASE(16)

@@ -58,6 +58,9 @@ struct KernelOptions {
     int iter_ilp = 1;          // pixels whose UpdateMatrices gathers a k_iter thread keeps in flight
     int iter_prefetch = 1;     // software L2 prefetch one step ahead in k_iter
     int polyexp_tma = 0;       // persistent TMA variant of the scale-0 polynomial expansion
+    int pyr_fused = 1;         // scales 1..3 of the pyramid in one pass over the frame (k_pyr_fused)
+    int polyexp_fast = 1;      // interior tiles of the polynomial expansion take pe_tile_fast (packed f32x2 vertical pass)
+    int f32_window_sums = 0;   // 1 = box-window sums in f32 (k_iter; faster, NOT within the parity tolerance on rank-deficient input)
 };
 
 struct Launch {

@@ -435,4 +435,165 @@ void launch_pyr2(Launch& L, int dtype, const PyrArgs& a, int batch)
     L.run("pyr_v", [&](cudaStream_t s) { k_pyr_v2<<<gv, block, 0, s>>>(a); });
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_pyr_fused: the level images of scales 1..3 of ONE frame tile in one pass over the frame (pyr_scale = 0.5, frame sizes that
+// are multiples of 8, u8 rows 4-byte aligned).  The per-level kernels above read the whole u8 frame once per level
+// (ncu: 3 x 2.07 MB per 1080p frame, plus the Hk x W intermediate written and read back) and were latency-bound on small
+// grids; here a CTA stages a 144 x 76 pixel patch of the frame in shared memory ONCE (as f32, reflect-101 applied while
+// staging, so the passes below have no border arithmetic) and produces from it the 64 x 32 tile of I_1, the 32 x 16 tile of
+// I_2 and the 16 x 8 tile of I_3 that depend on it.  Per level: the column pass at the sampled rows for every patch column
+// (4 columns per thread, 16-byte shared loads), a barrier, the row pass at the sampled columns.
+// Arithmetic and order are those of k_pyr_vf / k_pyr_hf (FMA per tap, the two bilinear weights at the end): bit-identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int PF_TX = 128, PF_TY = 64;           // frame pixels per CTA
+constexpr int PF_HX = 8, PF_HY = 6;              // halo: level 3 needs c + 1 = 10 columns beyond its sampled column 8x+3 -> 6 (+2 to stay 4-aligned)
+constexpr int PF_SW = PF_TX + 2 * PF_HX, PF_SH = PF_TY + 2 * PF_HY + 0;     // 144 x 76 staged pixels
+constexpr int PF_TP = PF_SW + 1;                 // pitch of the column-pass result (odd)
+constexpr int PF_THREADS = 256;
+
+struct PyrFusedArgs {
+    const void* src; size_t src_item, src_pitch;
+    int W, H, nlev;
+    int Wk[3], Hk[3], pitch[3];
+    const int* sx[3]; const float* ax[3]; const int* sy[3]; const float* ay[3];
+    float* I[3]; size_t i_item[3];
+    float taps1[3], taps2[9], taps3[19];
+};
+
+template <int KS>
+__device__ __forceinline__ void pf_level(const PyrFusedArgs& a, const float (&taps)[KS], const int lv, const float* sS, float* sT,
+                                         const int cx0, const int cy0, const int bx, const int by, const int z)
+{
+    constexpr int c = KS / 2;
+    const int tw = PF_TX >> (lv + 1), th = PF_TY >> (lv + 1);           // output tile of this level
+    const int X0 = bx * tw, Y0 = by * th;
+    const int tid = threadIdx.x;
+    // column pass: item = (output row, group of 4 patch columns)
+    for (int i = tid; i < th * (PF_SW / 4); i += PF_THREADS) {
+        const int yl = i / (PF_SW / 4), xg = i - yl * (PF_SW / 4);
+        const int Y = Y0 + yl;
+        if (Y >= a.Hk[lv]) continue;
+        const int sy = a.sy[lv][Y];
+        const float a1 = a.ay[lv][Y], a0 = 1.f - a1;
+        const float* p = sS + (sy - c - cy0) * PF_SW + 4 * xg;
+        float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 o;
+        if (a1 != 0.f) {
+            float4 prev = *reinterpret_cast<const float4*>(p);
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                const float4 cur = *reinterpret_cast<const float4*>(p + (j + 1) * PF_SW);
+                b0[0] = fmaf(taps[j], prev.x, b0[0]); b0[1] = fmaf(taps[j], prev.y, b0[1]);
+                b0[2] = fmaf(taps[j], prev.z, b0[2]); b0[3] = fmaf(taps[j], prev.w, b0[3]);
+                b1[0] = fmaf(taps[j], cur.x, b1[0]); b1[1] = fmaf(taps[j], cur.y, b1[1]);
+                b1[2] = fmaf(taps[j], cur.z, b1[2]); b1[3] = fmaf(taps[j], cur.w, b1[3]);
+                prev = cur;
+            }
+            o = make_float4(fmaf(b1[0], a1, b0[0] * a0), fmaf(b1[1], a1, b0[1] * a0), fmaf(b1[2], a1, b0[2] * a0), fmaf(b1[3], a1, b0[3] * a0));
+        } else {
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                const float4 v = *reinterpret_cast<const float4*>(p + j * PF_SW);
+                b0[0] = fmaf(taps[j], v.x, b0[0]); b0[1] = fmaf(taps[j], v.y, b0[1]);
+                b0[2] = fmaf(taps[j], v.z, b0[2]); b0[3] = fmaf(taps[j], v.w, b0[3]);
+            }
+            o = make_float4(b0[0], b0[1], b0[2], b0[3]);
+        }
+        float* t = sT + yl * PF_TP + 4 * xg;
+        t[0] = o.x; t[1] = o.y; t[2] = o.z; t[3] = o.w;
+    }
+    __syncthreads();
+    // row pass: item = output pixel, lanes along x (coalesced stores)
+    float* out = a.I[lv] + (size_t)z * a.i_item[lv];
+    for (int i = tid; i < th * tw; i += PF_THREADS) {
+        const int yl = i / tw, xl = i - yl * tw;
+        const int X = X0 + xl, Y = Y0 + yl;
+        if (X >= a.Wk[lv] || Y >= a.Hk[lv]) continue;
+        const int sx = a.sx[lv][X];
+        const float a1 = a.ax[lv][X], a0 = 1.f - a1;
+        const float* p = sT + yl * PF_TP + (sx - c - cx0);
+        float b0 = 0.f, b1 = 0.f, r;
+        if (a1 != 0.f) {
+            float prev = p[0];
+#pragma unroll
+            for (int j = 0; j < KS; j++) {
+                const float cur = p[j + 1];
+                b0 = fmaf(taps[j], prev, b0);
+                b1 = fmaf(taps[j], cur, b1);
+                prev = cur;
+            }
+            r = __fadd_rn(__fmul_rn(b0, a0), __fmul_rn(b1, a1));
+        } else {
+#pragma unroll
+            for (int j = 0; j < KS; j++) b0 = fmaf(taps[j], p[j], b0);
+            r = b0;
+        }
+        out[(size_t)Y * a.pitch[lv] + X] = r;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PF_THREADS)
+k_pyr_fused(PyrFusedArgs a)
+{
+    extern __shared__ __align__(16) float pf_smem[];
+    float* sS = pf_smem;                          // PF_SH x PF_SW staged frame patch (f32)
+    float* sT = pf_smem + PF_SH * PF_SW;          // column-pass result of the current level: <= 32 x PF_TP
+    const int bx = blockIdx.x, by = blockIdx.y, z = blockIdx.z, tid = threadIdx.x;
+    const int cx0 = bx * PF_TX - PF_HX, cy0 = by * PF_TY - PF_HY;
+    const int W = a.W, H = a.H;
+    const unsigned char* src = (const unsigned char*)a.src + (size_t)z * a.src_item;
+    const bool inside = cx0 >= 0 && cx0 + PF_SW <= W && cy0 >= 0 && cy0 + PF_SH <= H;
+    if (inside) {
+        for (int i = tid; i < PF_SH * (PF_SW / 4); i += PF_THREADS) {
+            const int r = i / (PF_SW / 4), v = i - r * (PF_SW / 4);
+            const unsigned w = *reinterpret_cast<const unsigned*>(src + (size_t)(cy0 + r) * a.src_pitch + cx0 + 4 * v);
+            float4 o;
+            o.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u)) - 8388608.f;
+            o.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441u)) - 8388608.f;
+            o.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442u)) - 8388608.f;
+            o.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443u)) - 8388608.f;
+            *reinterpret_cast<float4*>(sS + r * PF_SW + 4 * v) = o;
+        }
+    } else {
+        for (int i = tid; i < PF_SH * PF_SW; i += PF_THREADS) {
+            const int r = i / PF_SW, cc = i - r * PF_SW;
+            const int fy = reflect101(cy0 + r, H), fx = reflect101(cx0 + cc, W);
+            sS[i] = u8_to_f32(src[(size_t)fy * a.src_pitch + fx]);
+        }
+    }
+    __syncthreads();
+    pf_level<3>(a, a.taps1, 0, sS, sT, cx0, cy0, bx, by, z);
+    if (a.nlev > 1) pf_level<9>(a, a.taps2, 1, sS, sT, cx0, cy0, bx, by, z);
+    if (a.nlev > 2) pf_level<19>(a, a.taps3, 2, sS, sT, cx0, cy0, bx, by, z);
+}
+
+// Conditions under which the sampled rows / columns of every tile stay inside the staged patch: pyr_scale 0.5 on frame sizes
+// that are multiples of 8 gives the affine tables sx = 2x (a 1/2), 4x+1, 8x+3 that the halo constants above are derived from.
+bool pyr_fused_supported(int dtype, int W, int H, double pyr_scale, const void* src, size_t src_pitch, size_t src_item)
+{
+    return dtype == 0 && pyr_scale == 0.5 && W % 8 == 0 && H % 8 == 0 && W >= 64 && H >= 64 && src_pitch % 4 == 0 && src_item % 4 == 0 &&
+           ((uintptr_t)src % 4) == 0;
+}
+
+void launch_pyr_fused(Launch& L, const PyrFusedLaunch& f, int batch)
+{
+    PyrFusedArgs a{};
+    a.src = f.src; a.src_item = f.src_item; a.src_pitch = f.src_pitch; a.W = f.W; a.H = f.H; a.nlev = f.nlev;
+    for (int k = 0; k < f.nlev; k++) {
+        a.Wk[k] = f.Wk[k]; a.Hk[k] = f.Hk[k]; a.pitch[k] = f.pitch[k];
+        a.sx[k] = f.sx[k]; a.ax[k] = f.ax[k]; a.sy[k] = f.sy[k]; a.ay[k] = f.ay[k];
+        a.I[k] = f.I[k]; a.i_item[k] = f.i_item[k];
+    }
+    for (int j = 0; j < 3; j++) a.taps1[j] = f.taps[0][j];
+    for (int j = 0; j < 9; j++) a.taps2[j] = f.taps[1][j];
+    for (int j = 0; j < 19; j++) a.taps3[j] = f.taps[2][j];
+    const size_t smem = sizeof(float) * (PF_SH * PF_SW + 32 * PF_TP);
+    static unsigned long long configured = 0;
+    L.dyn_smem(k_pyr_fused, smem, configured);
+    dim3 grid(divup(f.W, PF_TX), divup(f.H, PF_TY), batch);
+    L.run("pyr_fused", [&](cudaStream_t s) { k_pyr_fused<<<grid, PF_THREADS, smem, s>>>(a); });
+}
+
 }  // namespace ofb

@@ -138,6 +138,13 @@ class Farneback:
     def set_option(self, name, value):
         self._check(self._L.ofb_set_option(self._h, name.encode(), int(value)))
 
+    def check_guards(self):
+        """Number of overwritten guard bytes around the current workspaces (0 = no out-of-bounds write next to a buffer)."""
+        n = self._L.ofb_debug_check_guards(self._h)
+        if n < 0:
+            self._check(n)
+        return n
+
     def synchronize(self):
         self._check(self._L.ofb_synchronize(self._h))
 

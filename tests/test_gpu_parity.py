@@ -676,3 +676,50 @@ def test_degenerate_frames_through_the_shot_path(eng, oracle, kind):
     d = np.sqrt(((res["flow"][0].astype(np.float64) - ref) ** 2).sum(-1))
     assert np.median(d) <= 1e-4 and d.mean() <= 2e-2, (kind, float(np.median(d)), float(d.mean()), float(d.max()))
     assert np.array_equal(res["bgr"][0], oracle.viz(res["flow"][0], 0))
+
+
+# ------------------------------------------------------------------------------------------------
+# memory safety and races without compute-sanitizer (closed on the B200 pool; profiles/r2b_memcheck.out)
+# ------------------------------------------------------------------------------------------------
+def test_no_workspace_guard_band_is_overwritten():
+    """Every engine workspace carries a 256-byte guard band on both sides (engine.cu guarded_alloc).  After a workload that
+    exercises every fast-path kernel family on frames with interior and border tiles (tools/sanitize_case.py's list), no guard
+    byte may have changed: an out-of-bounds write next to a buffer -- the kind a halo / tile-edge bug makes -- shows up here."""
+    import optical_flow_b200 as ofb
+    eng = ofb.Farneback(0)
+    rng = np.random.default_rng(0)
+    ref = dict(ofb.REFERENCE_PARAMS)
+    for (W, H) in ((448, 200), (203, 97), (640, 360), (129, 72), (64, 64), (72, 136)):
+        fr = np.stack([_textured(W, H, 40 + t)[0] for t in range(5)])
+        for kw in (ref, dict(ref, winsize=9, iterations=2), dict(ref, flags=256, poly_n=7, poly_sigma=1.5), dict(ref, winsize=33)):
+            eng.shot(fr, want_bgr=True, want_magsum=True, want_flow=True, **kw)
+            assert eng.check_guards() == 0, (W, H, kw)
+        eng.pairs(fr[:-1], fr[1:], want_magsum=True, **ref)
+        eng.shot_jpeg(fr, **ref)
+        f = eng.calc(fr[0], fr[1], None, **ref)
+        eng.calc(fr[0], fr[1], f.copy(), **dict(ref, flags=4))
+        eng.calc(fr[0].astype(np.float32), fr[1].astype(np.float32), None, **ref)
+        assert eng.check_guards() == 0, (W, H)
+    bgr = rng.integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    eng.shot_bgr(bgr, dsize=(129, 96), want_bgr=True, want_magsum=True, want_gray=True)
+    assert eng.check_guards() == 0
+
+
+def test_repeated_runs_are_bitwise_identical(eng):
+    """k_iter / k_iter64 reuse shared memory across steps with one barrier fewer than phases, k_polyexp2 aliases its staging
+    buffers, the JPEG emit kernel combines words with atomicOr: a race would show as run-to-run differences.  Eight
+    repetitions of a shot with many strips and tiles must agree bit for bit, with the software prefetch on and off."""
+    f = _textured(640, 360, 77)[0]
+    frames = np.stack([np.roll(f, (t, 2 * t), (0, 1)) for t in range(6)])
+    ref = None
+    for rep in range(8):
+        eng.set_option("iter_prefetch", rep % 2)
+        try:
+            res = eng.shot(frames, want_bgr=True, want_flow=True, want_magsum=True)
+            jp = eng.shot_jpeg(frames)
+        finally:
+            eng.set_option("iter_prefetch", 1)
+        cur = (res["flow"].tobytes(), res["bgr"].tobytes(), res["magsum"].tobytes(), jp["jpeg"][:int(jp["sizes"].sum())].tobytes())
+        if ref is None:
+            ref = cur
+        assert cur == ref, rep
