@@ -105,6 +105,8 @@ int ofb_farneback_device(ofb_context* ctx, const void* d_prev, const void* d_nex
 
 /* ---- companions of the call (Appendix B of SURVEY.md) ---------------------- */
 int ofb_cart_to_polar_host(ofb_context* ctx, const float* flow, int W, int H, float* mag, float* ang);
+/* the same with cv2's angleInDegrees flag */
+int ofb_cart_to_polar_host2(ofb_context* ctx, const float* flow, int W, int H, float* mag, float* ang, int angle_in_degrees);
 int ofb_sum_magnitude_host(ofb_context* ctx, const float* flow, int W, int H, float* out);
 int ofb_flow_to_bgr_host(ofb_context* ctx, const float* flow, int W, int H, uint8_t* bgr);
 int ofb_flow_to_bgr_device(ofb_context* ctx, const float* d_flow, int W, int H, uint8_t* d_bgr);

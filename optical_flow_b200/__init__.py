@@ -45,15 +45,17 @@ def calcOpticalFlowFarneback(prev, next, flow, pyr_scale, levels, winsize, itera
 def cartToPolar(x, y, magnitude=None, angle=None, angleInDegrees=False):
     """Drop-in for cv2.cartToPolar(x, y) -> (magnitude, angle) as the reference calls it
     (optical_flow.py:61, visualize_optical_flow.py:48: x, y are the two planes of a flow field)."""
-    if angleInDegrees:
-        raise NotImplementedError("angleInDegrees=True is not on the reference's path")
     x = np.asarray(x, dtype=np.float32)
     y = np.asarray(y, dtype=np.float32)
     if x.shape != y.shape:
         raise error("x.size() == y.size() && x.type() == y.type()", func="cartToPolar")
     shp = x.shape
     fl = np.stack([x.reshape(-1), y.reshape(-1)], -1).reshape(1, -1, 2)
-    mag, ang = default_engine().cart_to_polar(fl)
+    mag, ang = default_engine().cart_to_polar(fl, angle_in_degrees=bool(angleInDegrees))
+    if magnitude is not None and isinstance(magnitude, np.ndarray) and magnitude.shape == shp and magnitude.dtype == np.float32:
+        magnitude[...] = mag.reshape(shp); mag = magnitude           # cv2 fills a correctly typed destination in place
+    if angle is not None and isinstance(angle, np.ndarray) and angle.shape == shp and angle.dtype == np.float32:
+        angle[...] = ang.reshape(shp); ang = angle
     return mag.reshape(shp), ang.reshape(shp)
 
 

@@ -72,6 +72,7 @@ def load():
     proto("ofb_farneback_host", i, vp, vp, vp, i, i, i, sz, sz, vp, pp)
     proto("ofb_farneback_device", i, vp, vp, vp, i, i, i, sz, sz, vp, pp)
     proto("ofb_cart_to_polar_host", i, vp, vp, i, i, vp, vp)
+    proto("ofb_cart_to_polar_host2", i, vp, vp, i, i, vp, vp, i)
     proto("ofb_sum_magnitude_host", i, vp, vp, i, i, vp)
     proto("ofb_flow_to_bgr_host", i, vp, vp, i, i, vp)
     proto("ofb_flow_to_bgr_device", i, vp, vp, i, i, vp)

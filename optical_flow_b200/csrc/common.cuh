@@ -209,7 +209,7 @@ void launch_sum_magnitude_batch(Launch& L, const float2* flow, size_t flow_item,
 void launch_minmax_mag(Launch& L, const float2* flow, size_t n, unsigned* minmax /* [2], pre-set */);
 void launch_minmax_reset(Launch& L, unsigned* minmax);
 void launch_flow_to_bgr(Launch& L, const float2* flow, size_t n, const unsigned* minmax, uint8_t* bgr, const unsigned* table = nullptr);
-void launch_cart_to_polar(Launch& L, const float2* flow, size_t n, float* mag, float* ang);
+void launch_cart_to_polar(Launch& L, const float2* flow, size_t n, float* mag, float* ang, bool degrees = false);
 void launch_sum_magnitude(Launch& L, const float2* flow, size_t n, double* acc /* pre-zeroed */, float* out);
 
 }  // namespace ofb

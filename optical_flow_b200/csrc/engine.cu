@@ -427,7 +427,7 @@ void expand_frames(ofb_context* ctx, Launch& L, const void* d_frames, size_t ite
                    int slot_step = 1)
 {
     Plan& pl = ctx->plan;
-    const bool fast = pl.fast_poly && !ctx->generic;
+    const bool fast = pl.fast_poly && !ctx->generic && !ctx->kopt.generic_polyexp;
     // scales 1..3 in one pass over the frames when the geometry allows it (pyramid.cu k_pyr_fused)
     int nfused = 0;
     if (fast && pl.pyr_fused && ctx->kopt.pyr_fused && pyr_fused_supported(pl.dtype, pl.W, pl.H, pl.p.pyr_scale, d_frames, pitch_bytes, item_bytes)) {
@@ -965,6 +965,11 @@ int ofb_sum_magnitude_host(ofb_context* ctx, const float* flow, int W, int H, fl
 
 int ofb_cart_to_polar_host(ofb_context* ctx, const float* flow, int W, int H, float* mag, float* ang)
 {
+    return ofb_cart_to_polar_host2(ctx, flow, W, H, mag, ang, 0);
+}
+
+int ofb_cart_to_polar_host2(ofb_context* ctx, const float* flow, int W, int H, float* mag, float* ang, int angle_in_degrees)
+{
     if (!ctx || !flow || !mag || !ang || W <= 0 || H <= 0) return fail(ctx, OFB_ERR_BAD_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     size_t n = (size_t)W * H;
@@ -975,7 +980,7 @@ int ofb_cart_to_polar_host(ofb_context* ctx, const float* flow, int W, int H, fl
     cudaStream_t s = ctx->s_compute;
     CU(cudaMemcpyAsync(df, flow, n * 8, cudaMemcpyHostToDevice, s));
     Launch L = make_launch(ctx, s);
-    launch_cart_to_polar(L, (const float2*)df, n, dm, da);
+    launch_cart_to_polar(L, (const float2*)df, n, dm, da, angle_in_degrees != 0);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(mag, dm, n * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(ang, da, n * 4, cudaMemcpyDeviceToHost, s));
@@ -1562,9 +1567,10 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!strcmp(name, "iter_ilp")) { ctx->kopt.iter_ilp = value; return OFB_OK; }
     if (!strcmp(name, "iter_prefetch")) { ctx->kopt.iter_prefetch = value; return OFB_OK; }
     if (!strcmp(name, "polyexp_tma")) { ctx->kopt.polyexp_tma = value; return OFB_OK; }
+    if (!strcmp(name, "generic_polyexp")) { ctx->kopt.generic_polyexp = value; return OFB_OK; }
     if (!strcmp(name, "pyr_fused")) { ctx->kopt.pyr_fused = value; return OFB_OK; }
     if (!strcmp(name, "polyexp_fast")) { ctx->kopt.polyexp_fast = value; return OFB_OK; }
-    if (!strcmp(name, "f32_window_sums")) { ctx->kopt.f32_window_sums = value; return OFB_OK; }
+    if (!strcmp(name, "exact_window_sums")) { ctx->kopt.exact_window_sums = value; return OFB_OK; }
     if (!strcmp(name, "hsv_table")) { ctx->use_hsv_table = value != 0; return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }

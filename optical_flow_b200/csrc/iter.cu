@@ -372,20 +372,24 @@ static void run_iter(Launch& L, IterArgs a, int batch)
 
 
 // ------------------------------------------------------------------------------------------------
-// k_iter64<M, FUSE>: the box-window iteration with the window sums and the 2x2 solve in FP64, as cv2 has them
-// (FarnebackUpdateFlow_Blur keeps double running sums and a double solve).
+// k_iter64<M, FUSE>: the box-window iteration with cv2's OWN arithmetic for the window sums and the solve (option
+// "exact_window_sums"): FarnebackUpdateFlow_Blur keeps, per column, ONE double running sum down the whole image,
+//     vsum = float(row0 * (m+2)) + rows 1..m-1;   for every row y:  vsum += float(row[min(y+m, H-1)] - row[max(y-m-1, 0)])
+// (the difference of the entering and the leaving row is formed in FLOAT before it is added to the double), double running
+// sums along x, and a double solve (restated in oracle/farneback_oracle.c orc_blur_solve_box).
 //
-// Why not f32: where the 15x15 neighbourhood holds a single edge direction the matrix [g11 g12; g12 g22] is rank-deficient
-// and det = g11*g22 - g12^2 cancels; a 1e-7 relative error in the SUMS (not in the solve) then moves the flow by
-// cond * 1e-7, and on clean edges cond reaches 1e5..1e7: the f32 van Herk sums of k_iter were up to 0.2 px (checkerboard)
-// and 0.9 px (perpendicular step edges) away from cv2 while cv2 and the f64 oracle agreed to 4e-3 / 2e-6
-// (profiles/r2c_benchpath_adversarial_f32sums.log).  Textured frames never showed it.
-//
-// Same strip walk as k_iter.  V phase: thread = (channel, column) keeps the last R = 2M+1 raw f32 values of its column in
-// registers and ONE running f64 window sum (cv2's own scheme; restarted at every strip), 2 DADD + 2 F2F per element.
-// H phase: thread = (channel, row, segment), van Herk in f64 out of shared memory.  S phase: thread = pixel, determinant and
-// numerators with DFMA, rounded to f32 only for the final quotient, then (FUSE) UpdateMatrices exactly as in k_iter.
-// Shared memory: 8 * 5R * (97 + TW + 1) bytes = 108 KB for winsize 15, two CTAs per SM.
+// Why it exists.  Where a window is rank-deficient (one edge direction, or the replicated rows at the bottom of a periodic
+// pattern) det = g11*g22 - g12^2 cancels completely and the flow cv2 returns is decided by the rounding history of ITS sums:
+// the float differences above leave a drift of ~1e-7 relative that grows down the column.  Any other summation -- the f32
+// van Herk sums of k_iter, or exact f64 sums -- is equally "right" and lands up to 0.2 px elsewhere on a 0/255 checkerboard
+// (19 000 pixels in the bottom 10 rows of a 1080p frame; cv2's own optimised and plain builds differ by 3e-3 there;
+// profiles/r2e_diag_stage_swap.log).  Reproducing cv2 on such input needs its arithmetic, including the drift, and the drift
+// needs the whole column: in this mode a CTA walks the FULL height of its 82-column tile (no strips).
+// Same phases as k_iter.  V phase: thread = (channel, column), 1 FADD + 1 F2F + 1 DADD per element.  H phase: thread =
+// (channel, row, segment), van Herk in f64 out of shared memory (order differs from cv2's running sum by 1e-16 relative).
+// S phase: thread = pixel, determinant and numerators with DFMA, rounded to f32 only for the final quotient, then (FUSE)
+// UpdateMatrices exactly as in k_iter.  Shared memory: 8 * 5R * (97 + TW + 1) bytes = 108 KB for winsize 15, two CTAs per SM.
+// Measured on B200 against k_iter: iter_fused +26 %, iter_last +42 % (f64 shared-memory traffic), whole step -13 %.
 // ------------------------------------------------------------------------------------------------
 template <int M, bool FUSE>
 __global__ void __launch_bounds__(IT_THREADS, (M <= 7) ? 2 : 1)
@@ -413,12 +417,19 @@ k_iter64(IterArgs a)
     const float* __restrict__ src = a.Min + (size_t)z * a.m_item + (size_t)vc * a.plane + gx;
     const int pitch = a.pitch;
 
-    float win[R];                                                      // rows y-M .. y+M of this column, raw
-    double S = 0.0;                                                    // their sum
+    // old[r] = the row that LEAVES the window when it moves down to row ys + r:  max(ys + r - M - 1, 0)
+    float old[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        win[i] = src[(size_t)min(max(ybeg - M + i, 0), H - 1) * pitch];
-        S += (double)win[i];
+    for (int i = 0; i < R; i++) old[i] = src[(size_t)min(max(ybeg - M - 1 + i, 0), H - 1) * pitch];
+    // S = cv2's vsum BEFORE row ybeg is processed.  At the top of the image that is float(row0 * (m+2)) + rows 1..m-1;
+    // a strip that starts lower (not used by the exact mode) starts from the plain sum of the window of row ybeg - 1.
+    double S;
+    if (ybeg == 0) {
+        S = (double)__fmul_rn(old[0], (float)(M + 2));
+        for (int y = 1; y < M; y++) S += (double)src[(size_t)min(y, H - 1) * pitch];
+    } else {
+        S = 0.0;
+        for (int j = ybeg - 1 - M; j <= ybeg - 1 + M; j++) S += (double)src[(size_t)min(max(j, 0), H - 1) * pitch];
     }
 
     RView R0{nullptr, nullptr, 0}, R1{nullptr, nullptr, 0};
@@ -436,20 +447,20 @@ k_iter64(IterArgs a)
 
     for (int ys = ybeg; ys < yend; ys += R) {
         // ---- V phase ----
-        float nb[R];                                                   // rows ys+M+1 .. ys+3M+1 enter the window during this step
-        if (ys + 3 * M + 1 < H) {
-            const float* pb = src + (size_t)(ys + M + 1) * pitch;
+        float nb[R];                                                   // rows ys+M .. ys+3M enter the window during this step
+        if (ys + 3 * M < H) {
+            const float* pb = src + (size_t)(ys + M) * pitch;
 #pragma unroll
             for (int r = 0; r < R; r++) nb[r] = pb[r * pitch];
         } else {
 #pragma unroll
-            for (int r = 0; r < R; r++) nb[r] = src[(size_t)min(ys + M + 1 + r, H - 1) * pitch];
+            for (int r = 0; r < R; r++) nb[r] = src[(size_t)min(ys + M + r, H - 1) * pitch];
         }
         if (a.prefetch && ys + R < yend) {
             const int yn = ys + R;
             if (tid < 5 * R * 4) {
                 const int c = tid / (R * 4), rem = tid - c * (R * 4), r = rem >> 2, l = rem & 3;
-                const int row = min(yn + M + 1 + r, H - 1);
+                const int row = min(yn + M + r, H - 1);
                 const int col = max(x0 - M, 0) + 32 * l;
                 if (col < pitch) {
                     const float* p = a.Min + (size_t)z * a.m_item + (size_t)c * a.plane + (size_t)row * pitch + col;
@@ -479,9 +490,9 @@ k_iter64(IterArgs a)
             double* v = sV + vc * R * IT_VP + vcol;
 #pragma unroll
             for (int r = 0; r < R; r++) {
+                S += (double)__fsub_rn(nb[r], old[r]);                 // cv2: vsum[x] += srow1[x] - srow0[x]  (float difference)
                 v[r * IT_VP] = S;                                      // window of row ys + r
-                S = (S + (double)nb[r]) - (double)win[r];              // slide down one row
-                win[r] = nb[r];
+                old[r] = nb[r];                                        // the rows that entered now leave during the next step
             }
         }
         __syncthreads();
@@ -517,7 +528,8 @@ k_iter64(IterArgs a)
             if (y < yend && x < W) {
                 const double* h = sH + r * HP + lx;
                 const double g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
-                // cv2: idet = 1 / (g11*g22 - g12^2 + 1e-3) on sums scaled by 1/w^2; here unscaled sums, c64 = 1e-3 * w^4
+                // cv2: idet = 1 / (g11*g22 - g12^2 + 1e-3) on sums scaled by 1/w^2; here unscaled sums, c64 = 1e-3 * w^4.  The
+                // three cancelling differences stay in f64 (DFMA); only the well-conditioned quotient is formed in f32.
                 const double det = fma(g11, g22, -(g12 * g12)) + c64;
                 const double nx = fma(g11, h2, -(g12 * h1));
                 const double ny = fma(g22, h1, -(g12 * h2));
@@ -562,13 +574,9 @@ static void run_iter64(Launch& L, IterArgs a, int batch)
     static unsigned long long configured = 0;
     L.dyn_smem(k_iter64<M, FUSE>, smem, configured);
     const int xt = divup(a.W, TW);
-    int want = std::max(1, (L.sm_count + xt - 1) / xt);      // same strip partition rule as run_iter (results must not depend on the batch)
-    int strip = divup(divup(a.H, want), R) * R;
-    strip = std::max(strip, std::min(a.H, 4 * R));
-    strip = divup(strip, R) * R;
-    a.strip_rows = strip;
+    a.strip_rows = divup(a.H, R) * R;                        // ONE strip: cv2's running sums (and their drift) run down the whole column
     a.prefetch = L.opt.iter_prefetch;
-    dim3 grid(batch, xt, divup(a.H, strip));
+    dim3 grid(batch, xt, 1);
     L.run(FUSE ? "iter_fused" : "iter_last", [&](cudaStream_t s) { k_iter64<M, FUSE><<<grid, IT_THREADS, smem, s>>>(a); });
 }
 
@@ -591,7 +599,7 @@ void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int ba
             default: return;
         }
     }
-    if (!L.opt.f32_window_sums) {
+    if (L.opt.exact_window_sums) {
         switch (m) {
 #define OFB_CASE(MM)                                                                          \
     case MM:                                                                                  \

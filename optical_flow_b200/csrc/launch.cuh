@@ -58,9 +58,11 @@ struct KernelOptions {
     int iter_ilp = 1;          // pixels whose UpdateMatrices gathers a k_iter thread keeps in flight
     int iter_prefetch = 1;     // software L2 prefetch one step ahead in k_iter
     int polyexp_tma = 0;       // persistent TMA variant of the scale-0 polynomial expansion
+    int generic_polyexp = 0;   // 1 = per-frame part (pyramid + polynomial expansion) through the simple kernels that keep cv2's exact float / double mix
     int pyr_fused = 1;         // scales 1..3 of the pyramid in one pass over the frame (k_pyr_fused)
     int polyexp_fast = 1;      // interior tiles of the polynomial expansion take pe_tile_fast (packed f32x2 vertical pass)
-    int f32_window_sums = 0;   // 1 = box-window sums in f32 (k_iter; faster, NOT within the parity tolerance on rank-deficient input)
+    int exact_window_sums = 0; // 1 = box-window sums with cv2's own arithmetic (k_iter64: double running sums of float differences down the
+                               // whole column, double solve): matches cv2 where windows are rank-deficient; ~13 % slower per step
 };
 
 struct Launch {

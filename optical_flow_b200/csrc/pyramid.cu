@@ -587,8 +587,8 @@ void launch_pyr_fused(Launch& L, const PyrFusedLaunch& f, int batch)
         a.I[k] = f.I[k]; a.i_item[k] = f.i_item[k];
     }
     for (int j = 0; j < 3; j++) a.taps1[j] = f.taps[0][j];
-    for (int j = 0; j < 9; j++) a.taps2[j] = f.taps[1][j];
-    for (int j = 0; j < 19; j++) a.taps3[j] = f.taps[2][j];
+    if (f.nlev > 1) for (int j = 0; j < 9; j++) a.taps2[j] = f.taps[1][j];
+    if (f.nlev > 2) for (int j = 0; j < 19; j++) a.taps3[j] = f.taps[2][j];
     const size_t smem = sizeof(float) * (PF_SH * PF_SW + 32 * PF_TP);
     static unsigned long long configured = 0;
     L.dyn_smem(k_pyr_fused, smem, configured);

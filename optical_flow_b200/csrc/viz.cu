@@ -178,13 +178,13 @@ k_flow_to_bgr_scalar(const float2* __restrict__ flow, size_t n, const unsigned* 
 }
 
 __global__ void __launch_bounds__(256)
-k_cart_to_polar(const float2* __restrict__ flow, size_t n, float* __restrict__ mag, float* __restrict__ ang)
+k_cart_to_polar(const float2* __restrict__ flow, size_t n, float* __restrict__ mag, float* __restrict__ ang, int degrees)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float2 f = flow[i];
         Polar p = polar_of(f.x, f.y);
         mag[i] = p.mag;
-        ang[i] = deg_to_rad_cv(p.ang_deg);
+        ang[i] = degrees ? p.ang_deg : deg_to_rad_cv(p.ang_deg);      // cv2: fastAtan2 gives degrees; radians = degrees * (pi/180)f
     }
 }
 
@@ -295,9 +295,9 @@ void launch_sum_magnitude_batch(Launch& L, const float2* flow, size_t flow_item,
     L.run("sum_finish", [&](cudaStream_t s) { k_sum_finish_batch<<<divup(batch, 64), 64, 0, s>>>(acc, out, batch); });
 }
 
-void launch_cart_to_polar(Launch& L, const float2* flow, size_t n, float* mag, float* ang)
+void launch_cart_to_polar(Launch& L, const float2* flow, size_t n, float* mag, float* ang, bool degrees)
 {
-    L.run("cart_to_polar", [&](cudaStream_t s) { k_cart_to_polar<<<reduce_grid(n, 4), 256, 0, s>>>(flow, n, mag, ang); });
+    L.run("cart_to_polar", [&](cudaStream_t s) { k_cart_to_polar<<<reduce_grid(n, 4), 256, 0, s>>>(flow, n, mag, ang, degrees ? 1 : 0); });
 }
 
 void launch_sum_magnitude(Launch& L, const float2* flow, size_t n, double* acc, float* out)

@@ -26,8 +26,16 @@ _ASSERT_FRAMES = ("prev0.size() == next0.size() && prev0.channels() == next0.cha
 _ASSERT_FLOW = "_flow0.size() == prev0.size() && _flow0.channels() == 2 && _flow0.depth() == CV_32F"
 
 
-class error(Exception):
-    """Mirror of cv2.error for the argument errors of calcOpticalFlowFarneback (code -215)."""
+try:                                    # cv2 is only used for its exception TYPE: `except cv2.error:` at a call site that switched to
+    import cv2 as _cv2                  # this package keeps working; nothing of cv2's arithmetic is reachable from here
+    _ErrorBase = _cv2.error
+except Exception:                       # pragma: no cover - cv2 missing
+    _ErrorBase = Exception
+
+
+class error(_ErrorBase):
+    """cv2.error for the argument errors of calcOpticalFlowFarneback (code -215): a subclass of the installed cv2's own
+    exception type when cv2 is importable, so existing `except cv2.error` handlers still catch it."""
 
     def __init__(self, msg, code=-215, func="calc"):
         super().__init__("OpenCV-compatible(%d) error: (%d:Assertion failed) %s in function '%s'" % (code, code, msg, func))
@@ -167,13 +175,13 @@ class Farneback:
         return out
 
     # -- companions ----------------------------------------------------------------------------------
-    def cart_to_polar(self, flow):
-        """cv2.cartToPolar(flow[...,0], flow[...,1]) -> (magnitude, angle[rad])."""
+    def cart_to_polar(self, flow, angle_in_degrees=False):
+        """cv2.cartToPolar(flow[...,0], flow[...,1], angleInDegrees=...) -> (magnitude, angle)."""
         flow = np.ascontiguousarray(flow, dtype=np.float32)
         H, W = flow.shape[:2]
         mag = np.empty((H, W), np.float32)
         ang = np.empty((H, W), np.float32)
-        self._check(self._L.ofb_cart_to_polar_host(self._h, _ptr(flow), W, H, _ptr(mag), _ptr(ang)), "cartToPolar")
+        self._check(self._L.ofb_cart_to_polar_host2(self._h, _ptr(flow), W, H, _ptr(mag), _ptr(ang), int(bool(angle_in_degrees))), "cartToPolar")
         return mag, ang
 
     def sum_magnitude(self, flow):

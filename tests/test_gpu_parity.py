@@ -25,12 +25,6 @@ def eng():
     return ofb.Farneback(0)
 
 
-@pytest.fixture(scope="module")
-def synth():
-    from oracle import synth as s
-    return s
-
-
 def _textured(W, H, seed):
     """cv2-free synthetic texture (smooth noise) so the stage tests do not depend on cv2."""
     rng = np.random.default_rng(seed)
