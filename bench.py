@@ -403,8 +403,9 @@ def run_shot(args, rank, local_rank, world):
                        "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": 4 * P}
     if hasattr(eng, "shot_jpeg"):
         jres = {}
+        jbuf = ofb.pinned_empty((P * (n // 2 + 4096),), np.uint8)      # half a byte per pixel: ~5x a flow picture at quality 95
         def jcall():
-            r = eng.shot_jpeg(frames, **PARAMS)
+            r = eng.shot_jpeg(frames, out=jbuf, **PARAMS)
             jres["bytes"] = int(r["sizes"].sum())
             return r
         t_ev_j, t_wall_j, _, _ = timed_host_leg(jcall, steps2, 2)
@@ -412,6 +413,14 @@ def run_shot(args, rank, local_rank, world):
                         "what": "visualize_optical_flow.py:57-58 delivery: the picture leaves the GPU as the baseline-JPEG "
                                 "byte stream cv2.imwrite would produce (quality 95, 4:2:0), frames H2D inside",
                         "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": jres.get("bytes")}
+    # the cv2-exact arithmetic mode (cv2's running sums and float / double mix; needed only where windows are rank-deficient)
+    eng.set_option("exact_arithmetic", 1)
+    try:
+        t_ev_x, t_wall_x, _, _ = timed_host_leg(lambda: eng.shot(frames, want_bgr=True, out_bgr=bgr_host, **PARAMS), steps2, 2)
+    finally:
+        eng.set_option("exact_arithmetic", 0)
+    legs["exact_arithmetic"] = {"value": pf / (t_ev_x / 1e3), "unit": UNIT,
+                                "what": "the raw-picture protocol with option exact_arithmetic = 1 (k_iter64 + cv2's polyexp mix)"}
     if args.motion == "smooth" and not args.no_rough:
         synth_frames.shot_rough(W, H, P + 1, seed=100 + rank, out=frames)
         t_ev_r, t_wall_r, _, _ = timed_host_leg(lambda: eng.shot(frames, want_bgr=True, out_bgr=bgr_host, **PARAMS), steps2, 2)
@@ -436,6 +445,14 @@ def run_shot(args, rank, local_rank, world):
         eng.reset_kernel_stats()
         eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
         stats = eng.kernel_stats()
+        if "jpeg" in legs:                          # the encoder's own kernels: CUDA events around each, one 48-pair pass
+            eng.reset_kernel_stats()
+            npj = min(P, 48)
+            eng.shot_jpeg(frames[:npj + 1], out=jbuf, **PARAMS)
+            js = {k: v for k, v in eng.kernel_stats().items() if k.startswith("jpeg_")}
+            legs["jpeg"]["encoder_us_per_picture"] = round(1e3 * sum(v[1] for v in js.values()) / npj, 2)
+            legs["jpeg"]["encoder_kernels_ms"] = {k: round(v[1], 3) for k, v in sorted(js.items(), key=lambda kv: -kv[1][1])}
+            legs["jpeg"]["encoder_pictures"] = npj
         eng.set_option("profile", 0)
         peak, peak_src = peaks()
         sched = ofb.scale_schedule(W, H, PARAMS["pyr_scale"], PARAMS["levels"])

@@ -702,6 +702,7 @@ int ensure_jpeg(ofb_context* ctx, int W, int H, int quality, int batch)
     CU(cudaMemcpy(q, &host_tab, sizeof(JpegTables), cudaMemcpyHostToDevice));
     w.tables = (const JpegTables*)q; w.header_len = host_tab.header_len;
     if (int rc = alloc((void**)&w.coef, B * g.nblk * 64 * sizeof(int16_t))) return rc;
+    if (int rc = alloc((void**)&w.blk_mask, B * g.nblk * sizeof(unsigned long long))) return rc;
     if (int rc = alloc((void**)&w.blk_bits, B * g.nblk * sizeof(uint32_t))) return rc;
     if (int rc = alloc((void**)&w.bits32, B * g.bits_cap + JPEG_SEG)) return rc;
     if (int rc = alloc((void**)&w.total_bits, B * sizeof(uint32_t))) return rc;
@@ -1168,13 +1169,16 @@ static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next
         if (magsum) launch_sum_magnitude_batch(L, pl.flow0[par], n, n, ctx->sumacc, d_sums + t0, b);
         CU(cudaEventRecord(ctx->ev_out_ready[par], sc));
         if (bgr || flow || want_jpeg) {
-            CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
+            if (!want_jpeg || bgr || flow) CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
             if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[par], (size_t)b * n * 3, cudaMemcpyDeviceToHost, sd));
             if (flow) CU(cudaMemcpyAsync(flow + (size_t)t0 * n * 2, pl.flow0[par], (size_t)b * n * 8, cudaMemcpyDeviceToHost, sd));
             if (want_jpeg) {
+                // first the streams of the PREVIOUS chunk (their size is known by now), so that their download does not queue
+                // behind this chunk's kernels on s_d2h; then the 16-byte read-back of this chunk's size
+                if (c >= 1) if (int rc = flush_jpeg(c - 1)) return rc;      // records ev_out_free of the previous chunk
+                CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
                 CU(cudaMemcpyAsync(ctx->h_tot + 2 * par, ctx->d_tot[par], 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sd));
                 CU(cudaEventRecord(ctx->ev_tot[par], sd));
-                if (c >= 1) if (int rc = flush_jpeg(c - 1)) return rc;      // records ev_out_free of the previous chunk
             } else {
                 CU(cudaEventRecord(ctx->ev_out_free[par], sd));
             }
@@ -1571,6 +1575,8 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!strcmp(name, "pyr_fused")) { ctx->kopt.pyr_fused = value; return OFB_OK; }
     if (!strcmp(name, "polyexp_fast")) { ctx->kopt.polyexp_fast = value; return OFB_OK; }
     if (!strcmp(name, "exact_window_sums")) { ctx->kopt.exact_window_sums = value; return OFB_OK; }
+    if (!strcmp(name, "polyexp_exact")) { ctx->kopt.polyexp_exact = value; return OFB_OK; }
+    if (!strcmp(name, "exact_arithmetic")) { ctx->kopt.exact_window_sums = ctx->kopt.polyexp_exact = (value != 0); return OFB_OK; }
     if (!strcmp(name, "hsv_table")) { ctx->use_hsv_table = value != 0; return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }

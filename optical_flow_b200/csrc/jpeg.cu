@@ -10,7 +10,8 @@
 //                  passes through shared memory, quantisation by 8q with an exact multiply-high reciprocal, zigzag;
 //                  coefficients leave as int16 in scan order (MCU-major, Y00 Y01 Y10 Y11 Cb Cr)
 //   k_jpeg_count   one thread per 8x8 block: length in bits of its Huffman code (DC difference against the previous block of
-//                  the same component, AC run/size pairs, ZRL, EOB)
+//                  the same component, AC run/size pairs, ZRL, EOB); the loop runs over the set bits of the block's
+//                  non-zero mask (built by k_jpeg_dct), i.e. once per non-zero coefficient
 //   k_jpeg_scan    one CTA per picture: exclusive prefix sum of the block lengths -> the bit offset of every block
 //   k_jpeg_emit    128 blocks per CTA: every thread writes its block's code at its bit offset into a shared-memory window
 //                  (atomicOr on the two words it shares with its neighbours), the window goes out as whole words
@@ -192,10 +193,13 @@ __device__ __forceinline__ void fdct8(int (&d)[8])
 
 // Picture z of the batch: (H, W, 3) uint8 BGR at bgr + z * bgr_item.  Output: coef + z * nblk * 64.
 __global__ void __launch_bounds__(DCT_THREADS)
-k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const JpegTables* __restrict__ tab, int16_t* __restrict__ coef)
+k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const JpegTables* __restrict__ tab, int16_t* __restrict__ coef,
+           unsigned long long* __restrict__ blk_mask)
 {
     __shared__ int sblk[24 * BLK_PITCH];                 // 4 MCUs x 6 blocks
     __shared__ __align__(16) int16_t sout[24 * 64];
+    __shared__ unsigned smask[24 * 2];                   // per block: bit k set <=> quantised coefficient at zigzag position k is non-zero
+    if (threadIdx.x < 48) smask[threadIdx.x] = 0u;
     const int tid = threadIdx.x;
     const int mx0 = blockIdx.x * 4, my = blockIdx.y, z = blockIdx.z;
     const int W = g.W, H = g.H;
@@ -265,14 +269,19 @@ k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const J
         for (int i = 0; i < 8; i++) d[i] = p[i * 8];
         fdct8<false>(d);
         const int c = (blk % 6) >= 4 ? 1 : 0;
+        unsigned m0 = 0u, m1 = 0u;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int nat = i * 8 + col;
             const int v = d[i];
             const unsigned a = (unsigned)abs(v) + tab->half[c][nat];
             const int qv = (int)__umulhi(a, tab->recip[c][nat]);                // (|v| + d/2) / d, exact
-            sout[blk * 64 + tab->zz_of_nat[nat]] = (int16_t)(v < 0 ? -qv : qv);
+            const int zz = tab->zz_of_nat[nat];
+            sout[blk * 64 + zz] = (int16_t)(v < 0 ? -qv : qv);
+            if (qv) { if (zz < 32) m0 |= 1u << zz; else m1 |= 1u << (zz - 32); }
         }
+        if (m0) atomicOr(&smask[blk * 2], m0);
+        if (m1) atomicOr(&smask[blk * 2 + 1], m1);
     }
     __syncthreads();
     // ---- dummy blocks (jccoefct.c): a luma block beyond the picture is all-zero AC with the DC of the preceding block ----
@@ -297,6 +306,12 @@ k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const J
         if (!real) v = (i & 31) == 0 ? (v & 0xffffu) : 0u;               // keep the propagated DC, zero every AC
         d32[i] = v;
     }
+    if (tid < nm * 6) {
+        const int m = tid / 6, b = tid - m * 6;
+        const bool real = b >= 4 || b == 0 || ((2 * (mx0 + m) + (b & 1)) < g.ywb && (2 * my + (b >> 1)) < g.yhb);
+        const unsigned long long mk = real ? ((unsigned long long)smask[tid * 2 + 1] << 32) | smask[tid * 2] : 0ull;
+        blk_mask[(size_t)z * g.nblk + ((size_t)my * g.mcux + mx0) * 6 + tid] = mk & ~1ull;      // AC positions only
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -316,18 +331,14 @@ __device__ __forceinline__ int dc_predictor(const int16_t* __restrict__ coef, in
     return prev < 0 ? 0 : (int)coef[(size_t)prev * 64];
 }
 
-struct Block64 { uint4 q[8]; };                          // 64 int16, zigzag order
-__device__ __forceinline__ int coef_at(const Block64& b, int k)
-{
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(b.q);
-    const uint32_t v = w[k >> 1];
-    return (int)(int16_t)((k & 1) ? (v >> 16) : (v & 0xffffu));
-}
-
 constexpr int HUF_THREADS = 128;
 
+// One thread per block.  The non-zero AC positions come as a 64-bit mask from k_jpeg_dct, so the loop runs once per NON-ZERO
+// coefficient (a dozen for a flow picture at quality 95) instead of 63 times with a divergent zero test; each coefficient is a
+// 2-byte load from the block's own 128-byte line.
 __global__ void __launch_bounds__(HUF_THREADS)
-k_jpeg_count(const int16_t* __restrict__ coef, JpegGeom g, const JpegTables* __restrict__ tab, uint32_t* __restrict__ blk_bits)
+k_jpeg_count(const int16_t* __restrict__ coef, const unsigned long long* __restrict__ blk_mask, JpegGeom g,
+             const JpegTables* __restrict__ tab, uint32_t* __restrict__ blk_bits)
 {
     __shared__ uint8_t slen[2][256];                     // AC code lengths
     for (int i = threadIdx.x; i < 512; i += HUF_THREADS) slen[i >> 8][i & 255] = (uint8_t)(tab->ac[i >> 8][i & 255] & 0xff);
@@ -336,25 +347,23 @@ k_jpeg_count(const int16_t* __restrict__ coef, JpegGeom g, const JpegTables* __r
     const int blk = blockIdx.x * HUF_THREADS + threadIdx.x;
     if (blk >= g.nblk) return;
     const int16_t* pc = coef + (size_t)z * g.nblk * 64;
+    const int16_t* mine = pc + (size_t)blk * 64;
     const int c = (blk % 6) >= 4 ? 1 : 0;
-    Block64 bk;
-    const uint4* src = reinterpret_cast<const uint4*>(pc + (size_t)blk * 64);
-#pragma unroll
-    for (int i = 0; i < 8; i++) bk.q[i] = src[i];
-    const int diff = coef_at(bk, 0) - dc_predictor(pc, blk);
+    unsigned long long m = blk_mask[(size_t)z * g.nblk + blk];
+    const int diff = (int)mine[0] - dc_predictor(pc, blk);
     int n = nbits_of(diff);
     unsigned bits = (tab->dc[c][n] & 0xff) + n;
-    int run = 0;
-#pragma unroll 1
-    for (int k = 1; k < 64; k++) {
-        const int v = coef_at(bk, k);
-        if (v == 0) { run++; continue; }
+    int prev = 0;
+    while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int run = k - prev - 1;
+        prev = k;
         bits += (run >> 4) * slen[c][0xf0];
-        n = nbits_of(v);
+        n = nbits_of((int)mine[k]);
         bits += slen[c][((run & 15) << 4) | n] + n;
-        run = 0;
     }
-    if (run > 0) bits += slen[c][0];
+    if (prev < 63) bits += slen[c][0];
     blk_bits[(size_t)z * g.nblk + blk] = bits;
 }
 
@@ -424,8 +433,8 @@ struct BitSink {
 };
 
 __global__ void __launch_bounds__(HUF_THREADS)
-k_jpeg_emit(const int16_t* __restrict__ coef, JpegGeom g, const JpegTables* __restrict__ tab, const uint32_t* __restrict__ blk_off,
-            const uint32_t* __restrict__ total_bits, uint32_t* __restrict__ bits32)
+k_jpeg_emit(const int16_t* __restrict__ coef, const unsigned long long* __restrict__ blk_mask, JpegGeom g, const JpegTables* __restrict__ tab,
+            const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ total_bits, uint32_t* __restrict__ bits32)
 {
     __shared__ uint32_t sac[2][256];
     __shared__ uint32_t win[EMIT_WORDS];
@@ -442,31 +451,30 @@ k_jpeg_emit(const int16_t* __restrict__ coef, JpegGeom g, const JpegTables* __re
     __syncthreads();
     if (blk < g.nblk) {
         const int16_t* pc = coef + (size_t)z * g.nblk * 64;
+        const int16_t* mine = pc + (size_t)blk * 64;
         const int c = (blk % 6) >= 4 ? 1 : 0;
-        Block64 bk;
-        const uint4* src = reinterpret_cast<const uint4*>(pc + (size_t)blk * 64);
-#pragma unroll
-        for (int i = 0; i < 8; i++) bk.q[i] = src[i];
+        unsigned long long m = blk_mask[(size_t)z * g.nblk + blk];
         const uint32_t p0 = off[blk] - (base_word << 5);             // bit position inside the window
         BitSink s{win, (int)(p0 >> 5), 0ull, (int)(p0 & 31), true};
-        const int diff = coef_at(bk, 0) - dc_predictor(pc, blk);
+        const int diff = (int)mine[0] - dc_predictor(pc, blk);
         int n = nbits_of(diff);
         const uint32_t dcode = tab->dc[c][n];
         s.put(dcode >> 8, (int)(dcode & 0xff));
         if (n) s.put((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << n) - 1), n);
-        int run = 0;
-#pragma unroll 1
-        for (int k = 1; k < 64; k++) {
-            const int v = coef_at(bk, k);
-            if (v == 0) { run++; continue; }
+        int prev = 0;
+        while (m) {
+            const int k = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            int run = k - prev - 1;
+            prev = k;
+            const int v = (int)mine[k];
             while (run > 15) { const uint32_t zc = sac[c][0xf0]; s.put(zc >> 8, (int)(zc & 0xff)); run -= 16; }
             n = nbits_of(v);
             const uint32_t ac = sac[c][(run << 4) | n];
             // code and value bits in one go (<= 16 + 10 bits)
             s.put(((ac >> 8) << n) | ((uint32_t)(v < 0 ? v - 1 : v) & ((1u << n) - 1)), (int)(ac & 0xff) + n);
-            run = 0;
         }
-        if (run > 0) { const uint32_t eob = sac[c][0]; s.put(eob >> 8, (int)(eob & 0xff)); }
+        if (prev < 63) { const uint32_t eob = sac[c][0]; s.put(eob >> 8, (int)(eob & 0xff)); }
         s.finish();
     }
     __syncthreads();
@@ -620,16 +628,16 @@ void launch_jpeg_encode(Launch& L, const JpegWork& w, const uint8_t* bgr, size_t
     const JpegGeom& g = w.geom;
     L.run("jpeg_dct", [&](cudaStream_t s) {
         dim3 grid(divup(g.mcux, 4), g.mcuy, batch);
-        k_jpeg_dct<<<grid, DCT_THREADS, 0, s>>>(bgr, bgr_item, g, w.tables, w.coef);
+        k_jpeg_dct<<<grid, DCT_THREADS, 0, s>>>(bgr, bgr_item, g, w.tables, w.coef, w.blk_mask);
     });
     L.run("jpeg_count", [&](cudaStream_t s) {
         dim3 grid(divup(g.nblk, HUF_THREADS), batch);
-        k_jpeg_count<<<grid, HUF_THREADS, 0, s>>>(w.coef, g, w.tables, w.blk_bits);
+        k_jpeg_count<<<grid, HUF_THREADS, 0, s>>>(w.coef, w.blk_mask, g, w.tables, w.blk_bits);
     });
     L.run("jpeg_scan", [&](cudaStream_t s) { k_jpeg_scan<<<batch, SCAN_THREADS, 0, s>>>(w.blk_bits, g, w.bits32, w.total_bits); });
     L.run("jpeg_emit", [&](cudaStream_t s) {
         dim3 grid(divup(g.nblk, HUF_THREADS), batch);
-        k_jpeg_emit<<<grid, HUF_THREADS, 0, s>>>(w.coef, g, w.tables, w.blk_bits, w.total_bits, w.bits32);
+        k_jpeg_emit<<<grid, HUF_THREADS, 0, s>>>(w.coef, w.blk_mask, g, w.tables, w.blk_bits, w.total_bits, w.bits32);
     });
     // the number of 4 KB segments a picture really has is only known on the device: launch for a bound derived from the
     // picture size (a q95 stream is far below 1 byte per pixel) and let empty segments return at once; the bound is checked

@@ -31,6 +31,7 @@ struct JpegWork {                            // device workspaces for `batch` pi
     const JpegTables* tables;
     int header_len;
     int16_t* coef;                           // batch x nblk x 64
+    unsigned long long* blk_mask;            // batch x nblk: bit k = AC coefficient at zigzag position k is non-zero
     uint32_t* blk_bits;                      // batch x nblk: code length, then bit offset
     uint32_t* bits32;                        // batch x bits_cap bytes
     uint32_t* total_bits;                    // batch

@@ -199,7 +199,7 @@ constexpr int PE_VG = PE_TH == 16 ? 3 : PE_TH == 32 ? 4 : 1, PE_VR = PE_TH == 16
 constexpr int PE_STAGE_PITCH = 64 + 32;      // TMA boxes start at x0-16: the innermost coordinate must be 16-byte aligned
 template <int N, int SRC>
 __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_smem, const int x0, const int y0, const int z,
-                                        const int staged_off)
+                                        const int staged_off, const bool exact = false)
 {
     constexpr int TW = PE_TW, TH = PE_TH;
     constexpr int PW = TW + 2 * N, PH = TH + 2 * N;
@@ -426,7 +426,53 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
     // One source array at a time, results reduced to f32 as soon as they are complete, to keep the register peak low.
     float o0[4], o1[4], o2[4], o3[4], o4[4];
     double c1[4];                                       // b1 * ig03, needed by o2 and o3
-    {
+    if (exact) {
+        // cv2's own float / double mix (FarnebackPolyExp; oracle/farneback_oracle.c orc_polyexp; k_polyexp_tiled): the sums and
+        // differences of the f32 rows are formed in FLOAT, four of the six products too, every accumulation is a separate
+        // double multiply and add.  The shared arrays hold the f32 vertical results widened exactly, so (float) gives them back.
+        float w[4 + 2 * N];
+        const double* q = sR0 + ly * RP + lx0;
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = (float)q[j];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double b1 = (double)__fmul_rn(w[o + N], a.g[0]), b2 = 0, b4 = 0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                const double tg = (double)__fadd_rn(w[o + N + k], w[o + N - k]);
+                b1 = __dadd_rn(b1, __dmul_rn(tg, a.gd[k]));
+                b4 = __dadd_rn(b4, __dmul_rn(tg, a.xxgd[k]));
+                b2 = __dadd_rn(b2, (double)__fmul_rn(__fsub_rn(w[o + N + k], w[o + N - k]), a.xg[k]));
+            }
+            c1[o] = __dmul_rn(b1, a.ig03);
+            o1[o] = (float)__dmul_rn(b2, a.ig11);
+            o3[o] = (float)__dadd_rn(c1[o], __dmul_rn(b4, a.ig33));
+        }
+        q = sR2 + ly * RP + lx0;
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = (float)q[j];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double b5 = (double)__fmul_rn(w[o + N], a.g[0]);
+#pragma unroll
+            for (int k = 1; k <= N; k++) b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(w[o + N + k], w[o + N - k]), a.g[k]));
+            o2[o] = (float)__dadd_rn(c1[o], __dmul_rn(b5, a.ig33));
+        }
+        q = sR1 + ly * RP + lx0;
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = (float)q[j];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double b3 = (double)__fmul_rn(w[o + N], a.g[0]), b6 = 0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(w[o + N + k], w[o + N - k]), a.g[k]));
+                b6 = __dadd_rn(b6, (double)__fmul_rn(__fsub_rn(w[o + N + k], w[o + N - k]), a.xg[k]));
+            }
+            o0[o] = (float)__dmul_rn(b3, a.ig11);
+            o4[o] = (float)__dmul_rn(b6, a.ig55);
+        }
+    } else {
         double w[4 + 2 * N];
         const double* q = sR0 + ly * RP + lx0;          // element j of the window = patch column lx0 + j
 #pragma unroll
@@ -722,6 +768,7 @@ k_polyexp2(PolyArgs a, int fast_path)
 {
     extern __shared__ __align__(128) unsigned char pe_smem[];
     const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH, z = blockIdx.z;
+    if (fast_path == 2) { pe_tile<N, SRC>(a, pe_smem, x0, y0, z, -1, true); return; }       // cv2's exact float / double mix, every tile
     if (SRC != 2 && PE_TH == 16 && fast_path) {                  // block-uniform: interior tiles take the lean path
         const unsigned char* srcb = (const unsigned char*)a.src + (size_t)z * a.src_item;
         if (pe_tile_is_interior<N, SRC>(a, x0, y0, srcb)) { pe_tile_fast<N, SRC == 2 ? 0 : SRC>(a, pe_smem, x0, y0, z); return; }
@@ -855,7 +902,7 @@ static bool run_polyexp2_tma(Launch& L, const PolyArgs& a, int batch)
 template <int N, int SRC>
 static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
 {
-    if (SRC == 1 && run_polyexp2_tma<N>(L, a, batch)) return;
+    if (SRC == 1 && !L.opt.polyexp_exact && run_polyexp2_tma<N>(L, a, batch)) return;
     constexpr int TW = PE_TW, TH = PE_TH, PW = TW + 2 * N, PH = TH + 2 * N, RP = (PW | 1);
     size_t smem = sizeof(double) * 3 * TH * RP +
                   sizeof(float) * (SRC == 0 ? (size_t)0 : (size_t)(PH + 2) * (PW + 2) + (size_t)(PH + 2) * PW);
@@ -863,7 +910,7 @@ static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
     L.dyn_smem(k_polyexp2<N, SRC>, smem, configured);
     dim3 grid(divup(a.W, TW), divup(a.H, TH), batch);
     const char* nm = SRC == 0 ? "polyexp_level" : "polyexp_scale0";
-    const int fast_path = L.opt.polyexp_fast && (SRC != 1 || ((a.W & 3) == 0 && (a.src_item & 3) == 0));
+    const int fast_path = L.opt.polyexp_exact ? 2 : (L.opt.polyexp_fast && (SRC != 1 || ((a.W & 3) == 0 && (a.src_item & 3) == 0)) ? 1 : 0);
     L.run(nm, [&](cudaStream_t s) { k_polyexp2<N, SRC><<<grid, PE_THREADS, smem, s>>>(a, fast_path); });
 }
 

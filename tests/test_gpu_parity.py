@@ -40,6 +40,41 @@ def _textured(W, H, seed):
 # ------------------------------------------------------------------------------------------------
 # per-stage parity against the oracle
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,sigma", [(5, 1.2), (7, 1.5), (3, 0.0)])
+def test_stage_polyexp_exact_mode_is_bit_identical_to_the_oracle(eng, oracle, n, sigma):
+    """Option "polyexp_exact": the batched kernel with cv2's own float / double mix in the horizontal pass (float sums and
+    differences, four float products, separate double multiply and add) gives the oracle's R bit for bit."""
+    f0, _ = _textured(203, 97, 2)
+    img = oracle.gaussian_blur(f0.astype(np.float32), 3, 0.0)
+    eng.set_option("polyexp_exact", 1)
+    try:
+        got = eng.stage_polyexp(img, n, sigma)
+    finally:
+        eng.set_option("polyexp_exact", 0)
+    assert np.array_equal(got, oracle.polyexp(img, n, sigma)), float(np.abs(got - oracle.polyexp(img, n, sigma)).max())
+
+
+@pytest.mark.parametrize("winsize", [3, 9, 15, 16, 33])
+def test_stage_blur_solve_exact_mode_follows_cv2_running_sums(eng, oracle, winsize):
+    """Option "exact_window_sums" (k_iter64): the oracle's flow to f32 rounding even on a matrix field whose windows are
+    exactly rank-deficient (one edge direction), where the default f32 sums differ visibly."""
+    rng = np.random.default_rng(winsize)
+    H, W = 150, 203
+    ys, xs = np.mgrid[0:H, 0:W]
+    gx = np.where((xs // 12) % 2 == 0, 80.0, -80.0).astype(np.float32)          # a pure-x pattern: G is rank 1 everywhere
+    M = np.zeros((H, W, 5), np.float32)
+    M[..., 0] = gx * gx; M[..., 3] = gx * 0.37
+    M += rng.random((H, W, 5)).astype(np.float32) * 1e-3
+    ref = oracle.blur_solve(M, winsize)
+    eng.set_option("exact_window_sums", 1)
+    try:
+        got = eng.stage_blur_solve(M, winsize)
+    finally:
+        eng.set_option("exact_window_sums", 0)
+    err = np.abs(got - ref).max()
+    assert err <= 1e-5 * max(1.0, float(np.abs(ref).max())), (winsize, float(err))
+
+
 @pytest.mark.parametrize("W,H,pyr,levels", [(320, 180, 0.5, 3), (129, 77, 0.5, 3), (200, 150, 0.7, 4), (640, 360, 0.5, 3)])
 def test_stage_level_image(eng, oracle, W, H, pyr, levels):
     f0, _ = _textured(W, H, 1)
@@ -586,12 +621,14 @@ def test_polyexp_tma_path_is_bit_identical(eng):
     default kernel (same arithmetic; only where the raw patch comes from differs), on a frame with interior and border tiles."""
     f = _textured(448, 200, 5)[0]
     frames = np.stack([np.roll(f, (i, 2 * i), (0, 1)) for i in range(4)])
-    ref = eng.shot(frames, want_bgr=True, want_flow=True)
-    eng.set_option("polyexp_tma", 1)
-    try:
+    eng.set_option("polyexp_fast", 0)                 # the TMA kernel runs pe_tile's arithmetic (interior tiles of the default path
+    try:                                              # use FFMA2 in the vertical pass, <= 1 ulp away)
+        ref = eng.shot(frames, want_bgr=True, want_flow=True)
+        eng.set_option("polyexp_tma", 1)
         got = eng.shot(frames, want_bgr=True, want_flow=True)
     finally:
         eng.set_option("polyexp_tma", 0)
+        eng.set_option("polyexp_fast", 1)
     assert np.array_equal(got["flow"], ref["flow"])
     assert np.array_equal(got["bgr"], ref["bgr"])
 

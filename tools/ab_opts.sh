@@ -17,7 +17,7 @@ try:
     d = json.loads(open("gpurun_out/abo_%s.json" % v).read().strip().splitlines()[-1])
     legs = d.get("legs", {})
     print(v, "proto", round(d["value"]), "dev", round(d["device_resident"]["value"]), "feature", round(legs.get("feature", {}).get("value", 0)),
-          "jpeg", round(legs.get("jpeg", {}).get("value", 0)), {k: round(x["total_ms"], 2) for k, x in d["kernels"].items() if x["total_ms"] > 0.25},
+          "jpeg", round(legs.get("jpeg", {}).get("value", 0)), legs.get("jpeg", {}).get("encoder_us_per_picture"), legs.get("jpeg", {}).get("encoder_kernels_ms"), {k: round(x["total_ms"], 2) for k, x in d["kernels"].items() if x["total_ms"] > 0.25},
           d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 except Exception as e:
     print(v, "FAILED", e); print(open("gpurun_out/abo_%s.err" % v).read()[-1500:])
