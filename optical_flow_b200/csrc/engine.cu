@@ -704,6 +704,7 @@ int ensure_jpeg(ofb_context* ctx, int W, int H, int quality, int batch)
     if (int rc = alloc((void**)&w.coef, B * g.nblk * 64 * sizeof(int16_t))) return rc;
     if (int rc = alloc((void**)&w.blk_mask, B * g.nblk * sizeof(unsigned long long))) return rc;
     if (int rc = alloc((void**)&w.blk_bits, B * g.nblk * sizeof(uint32_t))) return rc;
+    if (int rc = alloc((void**)&w.cta_bits, B * ((size_t)g.nblk / 128 + 2) * sizeof(uint32_t))) return rc;
     if (int rc = alloc((void**)&w.bits32, B * g.bits_cap + JPEG_SEG)) return rc;
     if (int rc = alloc((void**)&w.total_bits, B * sizeof(uint32_t))) return rc;
     if (int rc = alloc((void**)&w.seg_ff, B * g.nseg_cap * sizeof(uint32_t))) return rc;

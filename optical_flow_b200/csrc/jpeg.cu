@@ -213,6 +213,19 @@ k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const J
         // the 2x2 box and ROWS after it: chroma row cy >= ch_real is a copy of chroma row ch_real - 1.
         const int cyc = min(cy, g.ch_real - 1);
         int yv[4], cb = 0, cr = 0;
+        if (2 * cx + 1 < W && 2 * cy + 1 < H && (W & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 1) == 0) {
+            // interior quad of an even-width picture: its two pixel pairs are 6 contiguous, 2-byte aligned bytes per row
+#pragma unroll
+            for (int dy = 0; dy < 2; dy++) {
+                const unsigned short* p = reinterpret_cast<const unsigned short*>(src + ((size_t)(2 * cy + dy) * W + 2 * cx) * 3);
+                const unsigned h0 = p[0], h1 = p[1], h2 = p[2];                 // B0 G0 | R0 B1 | G1 R1
+                const int b0 = h0 & 255, g0 = h0 >> 8, r0 = h1 & 255, b1 = h1 >> 8, g1 = h2 & 255, r1 = h2 >> 8;
+                yv[2 * dy] = ((19595 * r0 + 38470 * g0 + 7471 * b0 + 32768) >> 16) - 128;
+                yv[2 * dy + 1] = ((19595 * r1 + 38470 * g1 + 7471 * b1 + 32768) >> 16) - 128;
+                cb += ((-11059 * r0 - 21709 * g0 + 32768 * b0 + (128 << 16) + 32767) >> 16) + ((-11059 * r1 - 21709 * g1 + 32768 * b1 + (128 << 16) + 32767) >> 16);
+                cr += ((32768 * r0 - 27439 * g0 - 5329 * b0 + (128 << 16) + 32767) >> 16) + ((32768 * r1 - 27439 * g1 - 5329 * b1 + (128 << 16) + 32767) >> 16);
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int dx = i & 1, dy = i >> 1;
@@ -234,6 +247,7 @@ k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const J
                 cb += (-11059 * r - 21709 * gg + 32768 * b + (128 << 16) + 32767) >> 16;
                 cr += (32768 * r - 27439 * gg - 5329 * b + (128 << 16) + 32767) >> 16;
             }
+        }
         }
         const int bias = 1 + (cx & 1);
         cb = ((cb + bias) >> 2) - 128;
@@ -367,45 +381,58 @@ k_jpeg_count(const int16_t* __restrict__ coef, const unsigned long long* __restr
     blk_bits[(size_t)z * g.nblk + blk] = bits;
 }
 
-// One CTA per picture: blk_bits (lengths) -> exclusive prefix (bit offsets), total bits of the picture; also zeroes the words of
-// the unstuffed stream that two CTAs of k_jpeg_emit share (they are written with atomicOr) and the last, partly used word.
+// Sum of the code lengths of the 128 blocks of every emit CTA (grid = CTAs x pictures): the input of k_jpeg_scan.
+__global__ void __launch_bounds__(HUF_THREADS)
+k_jpeg_ctasum(const uint32_t* __restrict__ blk_bits, JpegGeom g, int ncta, uint32_t* __restrict__ cta_bits)
+{
+    __shared__ uint32_t sw[HUF_THREADS / 32];
+    const int z = blockIdx.y, blk = blockIdx.x * HUF_THREADS + threadIdx.x;
+    uint32_t v = blk < g.nblk ? blk_bits[(size_t)z * g.nblk + blk] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) cta_bits[(size_t)z * ncta + blockIdx.x] = sw[0] + sw[1] + sw[2] + sw[3];
+}
+
+// One CTA per picture: exclusive prefix sum of the per-CTA code lengths (a few hundred values) -> the bit offset of every emit
+// CTA and the total of the picture; also zeroes the words of the unstuffed stream that two emit CTAs share (they are written
+// with atomicOr) and the last, partly used word.
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_jpeg_scan(uint32_t* __restrict__ blk_bits, JpegGeom g, uint32_t* __restrict__ bits32, uint32_t* __restrict__ total_bits)
+k_jpeg_scan(uint32_t* __restrict__ cta_bits, int ncta, JpegGeom g, uint32_t* __restrict__ bits32, uint32_t* __restrict__ total_bits)
 {
     __shared__ uint32_t swarp[32];
-    const int z = blockIdx.x, tid = threadIdx.x;
-    uint32_t* a = blk_bits + (size_t)z * g.nblk;
+    __shared__ uint32_t stot;
+    const int z = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t* a = cta_bits + (size_t)z * ncta;
     uint32_t* stream = bits32 + (size_t)z * (g.bits_cap / 4);
-    const int per = (g.nblk + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int i0 = min(tid * per, g.nblk), i1 = min(i0 + per, g.nblk);
-    uint32_t s = 0;
-    for (int i = i0; i < i1; i++) s += a[i];
-    // CTA-wide exclusive scan of the per-thread sums
-    const int lane = tid & 31, w = tid >> 5;
-    uint32_t inc = s;
+    uint32_t carry = 0;
+    for (int s0 = 0; s0 < ncta; s0 += SCAN_THREADS) {
+        const int i = s0 + tid;
+        const uint32_t v = i < ncta ? a[i] : 0u;
+        uint32_t inc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    if (lane == 31) swarp[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t v = swarp[lane], iv = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        __syncthreads();
+        if (lane == 31) swarp[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t x = swarp[lane], ix = x;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
-        swarp[lane] = iv - v;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, ix, o); if (lane >= o) ix += u; }
+            swarp[lane] = ix - x;
+            if (lane == 31) stot = ix;
+        }
+        __syncthreads();
+        if (i < ncta) {
+            const uint32_t off = carry + swarp[w] + inc - v;
+            a[i] = off;
+            stream[off >> 5] = 0u;                                     // first word of emit CTA i (shared with CTA i-1 when off % 32 != 0)
+        }
+        carry += stot;
     }
-    __syncthreads();
-    uint32_t run = swarp[w] + inc - s;
-    for (int i = i0; i < i1; i++) {
-        const uint32_t len = a[i];
-        a[i] = run;
-        if ((i % HUF_THREADS) == 0) stream[run >> 5] = 0u;            // first word of an emit CTA (shared with the previous one
-        run += len;                                                   // whenever the boundary falls inside a word)
-    }
-    if (tid == SCAN_THREADS - 1) {
-        total_bits[z] = run;
-        stream[run >> 5] = 0u;
-    }
+    if (tid == 0) { total_bits[z] = carry; stream[carry >> 5] = 0u; }
 }
 
 // 128 consecutive blocks per CTA.  Every thread encodes its block MSB-first into a shared-memory window that starts at the
@@ -434,27 +461,34 @@ struct BitSink {
 
 __global__ void __launch_bounds__(HUF_THREADS)
 k_jpeg_emit(const int16_t* __restrict__ coef, const unsigned long long* __restrict__ blk_mask, JpegGeom g, const JpegTables* __restrict__ tab,
-            const uint32_t* __restrict__ blk_off, const uint32_t* __restrict__ total_bits, uint32_t* __restrict__ bits32)
+            const uint32_t* __restrict__ blk_bits, const uint32_t* __restrict__ cta_off, int ncta, uint32_t* __restrict__ bits32)
 {
     __shared__ uint32_t sac[2][256];
     __shared__ uint32_t win[EMIT_WORDS];
-    const int tid = threadIdx.x, z = blockIdx.y;
+    __shared__ uint32_t swsum[HUF_THREADS / 32];
+    const int tid = threadIdx.x, z = blockIdx.y, lane = tid & 31;
     for (int i = tid; i < 512; i += HUF_THREADS) sac[i >> 8][i & 255] = tab->ac[i >> 8][i & 255];
     for (int i = tid; i < EMIT_WORDS; i += HUF_THREADS) win[i] = 0u;
     const int blk0 = blockIdx.x * HUF_THREADS;
     const int blk = blk0 + tid;
-    const uint32_t* off = blk_off + (size_t)z * g.nblk;
-    const uint32_t base_bit = off[blk0];
-    const int nlast = min(blk0 + HUF_THREADS, g.nblk);
-    const uint32_t end_bit = nlast < g.nblk ? off[nlast] : total_bits[z];
+    // bit offset of every block of this CTA: the CTA's offset (k_jpeg_scan) + an exclusive scan of the 128 code lengths
+    const uint32_t mylen = blk < g.nblk ? blk_bits[(size_t)z * g.nblk + blk] : 0u;
+    uint32_t inc = mylen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) swsum[tid >> 5] = inc;
+    const uint32_t base_bit = cta_off[(size_t)z * ncta + blockIdx.x];
     const uint32_t base_word = base_bit >> 5;
     __syncthreads();
+    uint32_t myoff = base_bit + inc - mylen;
+    for (int i = 0; i < (tid >> 5); i++) myoff += swsum[i];
+    const uint32_t end_bit = base_bit + swsum[0] + swsum[1] + swsum[2] + swsum[3];
     if (blk < g.nblk) {
         const int16_t* pc = coef + (size_t)z * g.nblk * 64;
         const int16_t* mine = pc + (size_t)blk * 64;
         const int c = (blk % 6) >= 4 ? 1 : 0;
         unsigned long long m = blk_mask[(size_t)z * g.nblk + blk];
-        const uint32_t p0 = off[blk] - (base_word << 5);             // bit position inside the window
+        const uint32_t p0 = myoff - (base_word << 5);                // bit position inside the window
         BitSink s{win, (int)(p0 >> 5), 0ull, (int)(p0 & 31), true};
         const int diff = (int)mine[0] - dc_predictor(pc, blk);
         int n = nbits_of(diff);
@@ -538,47 +572,39 @@ __global__ void __launch_bounds__(1024)
 k_jpeg_layout(uint32_t* __restrict__ seg_ff, JpegGeom g, const uint32_t* __restrict__ total_bits, int header_len, int batch, int nseg_launched,
               unsigned long long* __restrict__ out_off, uint32_t* __restrict__ sizes, unsigned long long* __restrict__ chunk_total)
 {
-    __shared__ uint32_t swarp[32];
-    __shared__ uint32_t stot;
-    __shared__ unsigned long long srun;
+    extern __shared__ unsigned long long ssize[];        // batch stream sizes
+    __shared__ unsigned sflag;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) srun = 0ull;
-    unsigned flag = 0;
-    for (int z = 0; z < batch; z++) {
+    if (tid == 0) sflag = 0u;
+    __syncthreads();
+    for (int z = w; z < batch; z += 32) {                // one warp per picture: exclusive prefix of its segments' 0xFF counts
         const uint32_t nbytes = stream_bytes(total_bits[z]);
         const int nseg = (int)((nbytes + JPEG_SEG - 1) / JPEG_SEG);
         uint32_t* a = seg_ff + (size_t)z * g.nseg_cap;
         uint32_t carry = 0;
-        for (int s0 = 0; s0 < nseg; s0 += 1024) {
-            const int i = s0 + tid;
-            const uint32_t v = i < nseg ? a[i] : 0u;
+        const int nscan = min(nseg, nseg_launched);
+        for (int s0 = 0; s0 < nscan; s0 += 32) {
+            const int i = s0 + lane;
+            const uint32_t v = i < nscan ? a[i] : 0u;
             uint32_t inc = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-            __syncthreads();                                  // swarp / stot of the previous round are no longer read
-            if (lane == 31) swarp[w] = inc;
-            __syncthreads();
-            if (w == 0) {
-                uint32_t x = swarp[lane], ix = x;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, ix, o); if (lane >= o) ix += u; }
-                swarp[lane] = ix - x;
-                if (lane == 31) stot = ix;
-            }
-            __syncthreads();
-            if (i < nseg) a[i] = carry + swarp[w] + inc - v;
-            carry += stot;
+            if (i < nscan) a[i] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (tid == 0) {
+        if (lane == 0) {
             const unsigned long long sz = (unsigned long long)header_len + nbytes + carry + 2ull;
-            out_off[z] = srun;
+            ssize[z] = sz;
             sizes[z] = (uint32_t)sz;
-            srun += sz;
-            if (sz > g.out_cap || nseg > nseg_launched) flag = 1u;
+            if (sz > g.out_cap || nseg > nseg_launched) atomicOr(&sflag, 1u);
         }
-        __syncthreads();
     }
-    if (tid == 0) { chunk_total[0] = srun; chunk_total[1] = flag; }
+    __syncthreads();
+    if (tid == 0) {                                      // the pictures of the chunk back to back
+        unsigned long long run = 0ull;
+        for (int z = 0; z < batch; z++) { out_off[z] = run; run += ssize[z]; }
+        chunk_total[0] = run; chunk_total[1] = sflag;
+    }
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
@@ -634,10 +660,13 @@ void launch_jpeg_encode(Launch& L, const JpegWork& w, const uint8_t* bgr, size_t
         dim3 grid(divup(g.nblk, HUF_THREADS), batch);
         k_jpeg_count<<<grid, HUF_THREADS, 0, s>>>(w.coef, w.blk_mask, g, w.tables, w.blk_bits);
     });
-    L.run("jpeg_scan", [&](cudaStream_t s) { k_jpeg_scan<<<batch, SCAN_THREADS, 0, s>>>(w.blk_bits, g, w.bits32, w.total_bits); });
+    const int ncta = divup(g.nblk, HUF_THREADS);
+    L.run("jpeg_scan", [&](cudaStream_t s) {
+        k_jpeg_ctasum<<<dim3(ncta, batch), HUF_THREADS, 0, s>>>(w.blk_bits, g, ncta, w.cta_bits);
+        k_jpeg_scan<<<batch, SCAN_THREADS, 0, s>>>(w.cta_bits, ncta, g, w.bits32, w.total_bits);
+    });
     L.run("jpeg_emit", [&](cudaStream_t s) {
-        dim3 grid(divup(g.nblk, HUF_THREADS), batch);
-        k_jpeg_emit<<<grid, HUF_THREADS, 0, s>>>(w.coef, w.blk_mask, g, w.tables, w.blk_bits, w.total_bits, w.bits32);
+        k_jpeg_emit<<<dim3(ncta, batch), HUF_THREADS, 0, s>>>(w.coef, w.blk_mask, g, w.tables, w.blk_bits, w.cta_bits, ncta, w.bits32);
     });
     // the number of 4 KB segments a picture really has is only known on the device: launch for a bound derived from the
     // picture size (a q95 stream is far below 1 byte per pixel) and let empty segments return at once; the bound is checked
@@ -647,7 +676,7 @@ void launch_jpeg_encode(Launch& L, const JpegWork& w, const uint8_t* bgr, size_t
         k_jpeg_ffcount<<<dim3(nseg, batch), SEG_THREADS, 0, s>>>(w.bits32, g, w.total_bits, w.seg_ff);
     });
     L.run("jpeg_layout", [&](cudaStream_t s) {
-        k_jpeg_layout<<<1, 1024, 0, s>>>(w.seg_ff, g, w.total_bits, w.header_len, batch, nseg, w.out_off, sizes, chunk_total);
+        k_jpeg_layout<<<1, 1024, sizeof(unsigned long long) * (size_t)batch, s>>>(w.seg_ff, g, w.total_bits, w.header_len, batch, nseg, w.out_off, sizes, chunk_total);
     });
     L.run("jpeg_stuff", [&](cudaStream_t s) {
         k_jpeg_stuff<<<dim3(nseg, batch), SEG_THREADS, 0, s>>>(w.bits32, g, w.total_bits, w.seg_ff, w.out_off, w.tables, out);

@@ -32,7 +32,8 @@ struct JpegWork {                            // device workspaces for `batch` pi
     int header_len;
     int16_t* coef;                           // batch x nblk x 64
     unsigned long long* blk_mask;            // batch x nblk: bit k = AC coefficient at zigzag position k is non-zero
-    uint32_t* blk_bits;                      // batch x nblk: code length, then bit offset
+    uint32_t* blk_bits;                      // batch x nblk: code length in bits
+    uint32_t* cta_bits;                      // batch x ceil(nblk / 128): code length, then bit offset, of every emit CTA
     uint32_t* bits32;                        // batch x bits_cap bytes
     uint32_t* total_bits;                    // batch
     uint32_t* seg_ff;                        // batch x nseg_cap

@@ -470,6 +470,7 @@ __device__ __forceinline__ void pf_level(const PyrFusedArgs& a, const float (&ta
     const int X0 = bx * tw, Y0 = by * th;
     const int tid = threadIdx.x;
     // column pass: item = (output row, group of 4 patch columns)
+#pragma unroll 2
     for (int i = tid; i < th * (PF_SW / 4); i += PF_THREADS) {
         const int yl = i / (PF_SW / 4), xg = i - yl * (PF_SW / 4);
         const int Y = Y0 + yl;
@@ -506,6 +507,7 @@ __device__ __forceinline__ void pf_level(const PyrFusedArgs& a, const float (&ta
     __syncthreads();
     // row pass: item = output pixel, lanes along x (coalesced stores)
     float* out = a.I[lv] + (size_t)z * a.i_item[lv];
+#pragma unroll 2
     for (int i = tid; i < th * tw; i += PF_THREADS) {
         const int yl = i / tw, xl = i - yl * tw;
         const int X = X0 + xl, Y = Y0 + yl;
@@ -546,15 +548,29 @@ k_pyr_fused(PyrFusedArgs a)
     const unsigned char* src = (const unsigned char*)a.src + (size_t)z * a.src_item;
     const bool inside = cx0 >= 0 && cx0 + PF_SW <= W && cy0 >= 0 && cy0 + PF_SH <= H;
     if (inside) {
-        for (int i = tid; i < PF_SH * (PF_SW / 4); i += PF_THREADS) {
-            const int r = i / (PF_SW / 4), v = i - r * (PF_SW / 4);
-            const unsigned w = *reinterpret_cast<const unsigned*>(src + (size_t)(cy0 + r) * a.src_pitch + cx0 + 4 * v);
-            float4 o;
-            o.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u)) - 8388608.f;
-            o.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441u)) - 8388608.f;
-            o.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442u)) - 8388608.f;
-            o.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443u)) - 8388608.f;
-            *reinterpret_cast<float4*>(sS + r * PF_SW + 4 * v) = o;
+        constexpr int NITEM = PF_SH * (PF_SW / 4), NIT = (NITEM + PF_THREADS - 1) / PF_THREADS;
+        unsigned wv[NIT];
+#pragma unroll
+        for (int k = 0; k < NIT; k++) {                     // every load of the thread in flight before the first use
+            const int i = tid + k * PF_THREADS;
+            if (i < NITEM) {
+                const int r = i / (PF_SW / 4), v = i - r * (PF_SW / 4);
+                wv[k] = *reinterpret_cast<const unsigned*>(src + (size_t)(cy0 + r) * a.src_pitch + cx0 + 4 * v);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NIT; k++) {
+            const int i = tid + k * PF_THREADS;
+            if (i < NITEM) {
+                const int r = i / (PF_SW / 4), v = i - r * (PF_SW / 4);
+                const unsigned w = wv[k];
+                float4 o;
+                o.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u)) - 8388608.f;
+                o.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441u)) - 8388608.f;
+                o.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442u)) - 8388608.f;
+                o.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443u)) - 8388608.f;
+                *reinterpret_cast<float4*>(sS + r * PF_SW + 4 * v) = o;
+            }
         }
     } else {
         for (int i = tid; i < PF_SH * PF_SW; i += PF_THREADS) {
