@@ -638,22 +638,29 @@ def run_long_video(args, rank, local_rank, world):
     synth_frames.shot(W, H, bank_n, seed=1000 + rank, out=bank)
     bank_frames = [bank[i] for i in range(bank_n)]
     max_len = max((n for _, _, n in mine), default=1)
-    out = ofb.pinned_empty((max_len, H, W, 3), np.uint8)
+    jpeg = args.deliver == "jpeg"
+    out = ofb.pinned_empty((max_len * (W * H // 2 + 4096),), np.uint8) if jpeg else ofb.pinned_empty((max_len, H, W, 3), np.uint8)
+
+    def run_piece(frames_):
+        if jpeg:
+            return eng.shot_frames_jpeg(frames_, out=out, **PARAMS)
+        return eng.shot_frames(frames_, want_bgr=True, out_bgr=out, **PARAMS)
 
     def frame_list(shot, first, n):      # forward-backward walk through the bank: consecutive frames differ by one warp step
         idx = (np.arange(first, first + n + 1) + shot * 7) % (2 * bank_n - 2)
         idx = np.where(idx < bank_n, idx, 2 * bank_n - 2 - idx)
         return [bank_frames[i] for i in idx]
 
-    eng.shot_frames(frame_list(0, 0, 48), want_bgr=True, out_bgr=out, **PARAMS)       # warm-up: workspaces, clocks
+    run_piece(frame_list(0, 0, 48))                                                   # warm-up: workspaces, clocks
     eng.synchronize(); tsync(); dist.barrier()
     t0 = time.perf_counter()
     dev_ms, done, checksum = 0.0, 0, 0
     for (shot, first, n) in mine:
-        r = eng.shot_frames(frame_list(shot, first, n), want_bgr=True, out_bgr=out, **PARAMS)
+        r = run_piece(frame_list(shot, first, n))
         dev_ms += r["device_ms"]
         done += n
-        checksum = (checksum * 31 + int(out[n - 1, H // 2, W // 2].sum())) % 1000003
+        probe = int(r["sizes"].sum()) if jpeg else int(out[n - 1, H // 2, W // 2].sum())
+        checksum = (checksum * 31 + probe) % 1000003
     eng.synchronize()
     wall = time.perf_counter() - t0
     dist.barrier()
@@ -663,9 +670,9 @@ def run_long_video(args, rank, local_rank, world):
         print(json.dumps({"metric": METRIC, "value": total / t_wall, "unit": UNIT, "n_gpus": world, "higher_is_better": True,
                           "scaling": "strong", "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "configs[3]: %d pairs of %dx%d in %d shots of 50-400 pairs, whole shots sharded "
-                                                 "longest-first over %d GPU(s); raw BGR picture per pair D2H; frames uploaded from "
+                                                 "longest-first over %d GPU(s); %s per pair D2H; frames uploaded from "
                                                  "65 pinned decoder-style buffers per rank via ofb_shot_host_v"
-                                                 % (int(total), W, H, len(lengths), world)},
+                                                 % (int(total), W, H, len(lengths), world, "JPEG file" if jpeg else "raw BGR picture")},
                           "pairs": int(total), "value_clock": "host wall clock of the slowest rank, all shots",
                           "pairs_per_s_device_events": total / (t_dev / 1e3), "wall_s": t_wall,
                           "shots_on_rank0": len(mine), "checksums": [s[0] for s in sums]}), flush=True)
@@ -688,33 +695,48 @@ def run_sharded_shot(args, rank, local_rank, world):
     allf = synth_frames.shot(W, H, P + 1, seed=100)                  # every rank generates the same shot, keeps its range
     frames = ofb.pinned_empty((e - s + 1, H, W), np.uint8)
     frames[:] = allf[s:e + 1]
-    out = ofb.pinned_empty((e - s, H, W, 3), np.uint8)
+    jpeg = args.deliver == "jpeg"
+    out = ofb.pinned_empty(((e - s) * (W * H // 2 + 4096),), np.uint8) if jpeg else ofb.pinned_empty((e - s, H, W, 3), np.uint8)
+
+    def step():
+        if jpeg:
+            return eng.shot_jpeg(frames, out=out, **PARAMS)
+        return eng.shot(frames, want_bgr=True, out_bgr=out, **PARAMS)
 
     def sync():
         eng.synchronize(); tsync(); dist.barrier()
     for _ in range(args.warmup):
-        eng.shot(frames, want_bgr=True, out_bgr=out, **PARAMS)
+        step()
     sync()
     w0 = time.perf_counter()
     ms = 0.0
     for _ in range(args.steps):
-        ms += eng.shot(frames, want_bgr=True, out_bgr=out, **PARAMS)["device_ms"]
+        r = step()
+        ms += r["device_ms"]
     sync()
     wall = time.perf_counter() - w0
     t_ev, t_wall = dist.reduce_max(ms), dist.reduce_max(wall)
-    digest = int(hashlib.sha1(out.tobytes()).hexdigest()[:15], 16)
+    payload = out[:int(r["sizes"].sum())].tobytes() if jpeg else out.tobytes()
+    digest = int(hashlib.sha1(payload).hexdigest()[:15], 16)
     digests = dist.gather_ints([digest])
     if rank == 0:
         same = None
         if world > 1 and not args.no_parity:        # the unsharded shot on rank 0: shard r must reproduce its slice bit for bit
-            whole = eng.shot(allf, want_bgr=True, **PARAMS)["bgr"]
-            same = all(int(hashlib.sha1(whole[a:b].tobytes()).hexdigest()[:15], 16) == digests[r][0]
+            if jpeg:
+                wj = eng.shot_jpeg(allf, **PARAMS)
+                ends = np.concatenate([[0], np.cumsum(wj["sizes"], dtype=np.int64)])
+                piece = lambda a, b: wj["jpeg"][ends[a]:ends[b]].tobytes()
+            else:
+                whole = eng.shot(allf, want_bgr=True, **PARAMS)["bgr"]
+                piece = lambda a, b: whole[a:b].tobytes()
+            same = all(int(hashlib.sha1(piece(a, b)).hexdigest()[:15], 16) == digests[r][0]
                        for r in range(world) for (a, b) in [ofb.shard_pairs(P, world, r)])
         print(json.dumps({"metric": METRIC, "value": P * args.steps / (t_ev / 1e3), "unit": UNIT, "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ev / args.steps, "higher_is_better": True,
                           "scaling": "strong", "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "ONE %d-pair %dx%d shot split into %d contiguous pair ranges (+1 overlap frame each), "
-                                                 "H2D frames + D2H raw pictures inside the timed region" % (P, W, H, world)},
+                                                 "H2D frames + D2H %s inside the timed region"
+                                                 % (P, W, H, world, "JPEG files" if jpeg else "raw pictures")},
                           "e2e": {"value": P * args.steps / t_wall, "unit": UNIT, "clock": "host wall clock"},
                           "shards_equal_unsharded_bitwise": same}), flush=True)
     dist.barrier()
@@ -728,6 +750,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="shot", choices=["shot", "feature", "long_video", "sharded_shot"])
     ap.add_argument("--motion", default="smooth", choices=["smooth", "rough"])
+    ap.add_argument("--deliver", default="raw", choices=["raw", "jpeg"], help="long_video / sharded_shot: what leaves the GPU per pair")
     ap.add_argument("--pairs", type=int, default=300)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)

@@ -134,6 +134,9 @@ int ofb_shot_host_v(ofb_context* ctx, const uint8_t* const* frames, int n_frames
  * stream i (stream i starts at the sum of the sizes before it).  magsum may be NULL. */
 int ofb_shot_host_jpeg(ofb_context* ctx, const uint8_t* frames, int n_frames, int W, int H, const ofb_params* p, int quality,
                        uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms);
+/* ofb_shot_host_jpeg with the frames at separate addresses (as ofb_shot_host_v). */
+int ofb_shot_host_v_jpeg(ofb_context* ctx, const uint8_t* const* frames, int n_frames, int W, int H, const ofb_params* p, int quality,
+                         uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms);
 /* The same with decoded BGR frames as input (gray conversion / resize on the GPU, as ofb_shot_bgr_host). */
 int ofb_shot_bgr_host_jpeg(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames, int W, int H, int dW, int dH, const ofb_params* p,
                            int quality, uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms);

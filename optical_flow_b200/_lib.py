@@ -81,6 +81,7 @@ def load():
     proto("ofb_shot_host", i, vp, vp, i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_shot_host_v", i, vp, C.POINTER(vp), i, i, i, pp, vp, vp, vp, fp)
     proto("ofb_shot_host_jpeg", i, vp, vp, i, i, i, pp, i, vp, sz, vp, vp, fp)
+    proto("ofb_shot_host_v_jpeg", i, vp, C.POINTER(vp), i, i, i, pp, i, vp, sz, vp, vp, fp)
     proto("ofb_shot_bgr_host_jpeg", i, vp, vp, i, i, i, i, i, pp, i, vp, sz, vp, vp, fp)
     proto("ofb_jpeg_encode_host", i, vp, vp, i, i, i, i, vp, sz, vp)
     proto("ofb_stage_jpeg_coefficients", i, vp, vp, i, i, i, vp)

@@ -1225,6 +1225,16 @@ int ofb_shot_host_jpeg(ofb_context* ctx, const uint8_t* frames, int n_frames, in
     return host_impl(ctx, frames, nullptr, n_frames - 1, W, H, 0, 0, p, nullptr, magsum, nullptr, nullptr, device_ms, nullptr, &jo);
 }
 
+int ofb_shot_host_v_jpeg(ofb_context* ctx, const uint8_t* const* frames, int n_frames, int W, int H, const ofb_params* p, int quality,
+                         uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms)
+{
+    if (!frames) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer table");
+    for (int i = 0; i < n_frames; i++) if (!frames[i]) return fail(ctx, OFB_ERR_BAD_ARG, "null frame pointer");
+    if (!jpeg || !jpeg_sizes) return fail(ctx, OFB_ERR_BAD_ARG, "null jpeg output");
+    const JpegOut jo{jpeg, jpeg_cap, jpeg_sizes, quality};
+    return host_impl(ctx, nullptr, nullptr, n_frames - 1, W, H, 0, 0, p, nullptr, magsum, nullptr, nullptr, device_ms, frames, &jo);
+}
+
 int ofb_shot_bgr_host_jpeg(ofb_context* ctx, const uint8_t* bgr_frames, int n_frames, int W, int H, int dW, int dH, const ofb_params* p,
                            int quality, uint8_t* jpeg, size_t jpeg_cap, uint32_t* jpeg_sizes, float* magsum, float* device_ms)
 {

@@ -199,7 +199,15 @@ k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const J
     __shared__ int sblk[24 * BLK_PITCH];                 // 4 MCUs x 6 blocks
     __shared__ __align__(16) int16_t sout[24 * 64];
     __shared__ unsigned smask[24 * 2];                   // per block: bit k set <=> quantised coefficient at zigzag position k is non-zero
+    __shared__ uint32_t srecip[2][64];                   // the quantisation tables, once per CTA (3 table reads per coefficient)
+    __shared__ uint16_t shalf[2][64];
+    __shared__ uint8_t szz[64];
     if (threadIdx.x < 48) smask[threadIdx.x] = 0u;
+    if (threadIdx.x < 128) {
+        srecip[threadIdx.x >> 6][threadIdx.x & 63] = tab->recip[threadIdx.x >> 6][threadIdx.x & 63];
+        shalf[threadIdx.x >> 6][threadIdx.x & 63] = tab->half[threadIdx.x >> 6][threadIdx.x & 63];
+        if (threadIdx.x < 64) szz[threadIdx.x] = tab->zz_of_nat[threadIdx.x];
+    }
     const int tid = threadIdx.x;
     const int mx0 = blockIdx.x * 4, my = blockIdx.y, z = blockIdx.z;
     const int W = g.W, H = g.H;
@@ -288,9 +296,9 @@ k_jpeg_dct(const uint8_t* __restrict__ bgr, size_t bgr_item, JpegGeom g, const J
         for (int i = 0; i < 8; i++) {
             const int nat = i * 8 + col;
             const int v = d[i];
-            const unsigned a = (unsigned)abs(v) + tab->half[c][nat];
-            const int qv = (int)__umulhi(a, tab->recip[c][nat]);                // (|v| + d/2) / d, exact
-            const int zz = tab->zz_of_nat[nat];
+            const unsigned a = (unsigned)abs(v) + shalf[c][nat];
+            const int qv = (int)__umulhi(a, srecip[c][nat]);                    // (|v| + d/2) / d, exact
+            const int zz = szz[nat];
             sout[blk * 64 + zz] = (int16_t)(v < 0 ? -qv : qv);
             if (qv) { if (zz < 32) m0 |= 1u << zz; else m1 |= 1u << (zz - 32); }
         }

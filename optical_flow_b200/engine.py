@@ -320,6 +320,26 @@ class Farneback:
         self._check(self._L.ofb_stage_jpeg_coefficients(self._h, _ptr(pic), W, H, int(quality), _ptr(out)))
         return out
 
+    def shot_frames_jpeg(self, frame_list, quality=95, out=None, **params):
+        """`shot_jpeg` for frames in separate buffers (ofb_shot_host_v_jpeg)."""
+        n = len(frame_list)
+        if n < 2:
+            raise ValueError("need at least two frames")
+        H, W = frame_list[0].shape
+        for f in frame_list:
+            if f.shape != (H, W) or f.dtype != np.uint8 or not f.flags.c_contiguous:
+                raise ValueError("every frame must be a C-contiguous (H, W) uint8 array of the same size")
+        table = (C.c_void_p * n)(*[f.ctypes.data for f in frame_list])
+        prm = make_params(**{**REFERENCE_PARAMS, **params})
+        if out is None:
+            out = np.empty((n - 1) * (W * H + 4096), np.uint8)
+        sizes = np.zeros(n - 1, np.uint32)
+        dev_ms = C.c_float(0)
+        self._check(self._L.ofb_shot_host_v_jpeg(self._h, table, n, W, H, C.byref(prm), int(quality), _ptr(out), out.size, _ptr(sizes),
+                                                 None, C.byref(dev_ms)))
+        offsets = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.int64)])
+        return {"jpeg": out, "sizes": sizes, "offsets": offsets, "device_ms": float(dev_ms.value)}
+
     def pairs(self, prev_frames, next_frames, want_bgr=False, want_magsum=True, want_flow=False, **params):
         """n independent pairs (prev_frames[i], next_frames[i]) in one batched submission: the window loop of
         optical_flow.py:83-99 (its pairs need not share frames)."""

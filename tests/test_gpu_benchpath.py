@@ -250,3 +250,44 @@ def test_degenerate_frames_against_cv2(eng, cv2, kind):
     res = eng.shot(np.stack([base, nxt, base]), want_bgr=True, want_flow=True, **REF)
     from oracle import c_oracle
     assert np.array_equal(res["bgr"][0], c_oracle.viz(res["flow"][0], 0))
+
+
+def test_flat_regions_with_sensor_noise_where_cv2_itself_is_not_reproducible(eng, cv2):
+    """Large flat regions and long clean edges plus +-1..2 grey levels of camera noise.  In the flat parts the flow is driven by
+    the noise and is chaotic IN cv2: its optimised and its plain build (cv2.setUseOptimized) differ by up to several pixels on
+    0.3 % of this frame, and so does the oracle.  Parity can only be stated where cv2 reproduces itself: on those pixels both
+    modes of the engine hold the north_star tolerance up to the 99.9th percentile and on the mean; the rest is counted."""
+    from oracle import c_oracle
+    c_oracle.build()
+    rng = np.random.default_rng(12)
+    H, W = 1080, 1920
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+
+    def scene(dx, dy):
+        a = np.full((H, W), 60.0, np.float32)
+        a[(xs - dx) > 700] = 190.0                                            # a long vertical edge
+        a[((ys - dy) > 300) & ((ys - dy) < 420)] += 40.0                      # a horizontal band
+        a[(xs - dx - 300) ** 2 + (ys - dy - 700) ** 2 < 150 ** 2] = 230.0     # a disc
+        a[((xs - dx) * 0.6 + (ys - dy)) > 1500] = 20.0                        # a slanted edge
+        return a
+    f0 = cv2.GaussianBlur(scene(0.0, 0.0), (0, 0), 0.8) + rng.normal(0, 1.2, (H, W)).astype(np.float32)
+    f1 = cv2.GaussianBlur(scene(2.3, -1.4), (0, 0), 0.8) + rng.normal(0, 1.2, (H, W)).astype(np.float32)
+    f0, f1 = np.clip(np.round(f0), 0, 255).astype(np.uint8), np.clip(np.round(f1), 0, 255).astype(np.uint8)
+    cf, _ = _cv2_pair(cv2, f0, f1, REF)
+    cv2.setUseOptimized(False)
+    try:
+        cf_plain, _ = _cv2_pair(cv2, f0, f1, REF)
+    finally:
+        cv2.setUseOptimized(True)
+    ref = c_oracle.farneback(f0, f1, None, **REF)
+    dist = lambda a, b: np.sqrt(((a.astype(np.float64) - b) ** 2).sum(-1))
+    stable = (dist(cf_plain, cf) <= 1e-3) & (dist(ref, cf) <= 1e-3)
+    frames = np.stack([f0, f1, f0])
+    for name, exact in (("default", False), ("exact_arithmetic", True)):
+        d = dist(_flow_in_mode(eng, frames, REF, exact), cf)
+        print("noisy flat regions, %-16s vs cv2: mean %.2e, on cv2-stable px (%.4f of the frame): mean %.2e p99.9 %.2e max %.2e, beyond 1e-2: %d px | "
+              "cv2 plain vs optimised max %.2f px, oracle vs cv2 max %.2f px"
+              % (name, d.mean(), stable.mean(), d[stable].mean(), np.quantile(d[stable], 0.999), d[stable].max(), int((d[stable] > EPE_MAX_TOL).sum()),
+                 dist(cf_plain, cf).max(), dist(ref, cf).max()))
+        assert stable.mean() >= 0.98
+        assert d[stable].mean() <= EPE_MEAN_TOL and np.quantile(d[stable], 0.999) <= EPE_MAX_TOL, name
