@@ -1588,6 +1588,7 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!strcmp(name, "exact_window_sums")) { ctx->kopt.exact_window_sums = value; return OFB_OK; }
     if (!strcmp(name, "polyexp_exact")) { ctx->kopt.polyexp_exact = value; return OFB_OK; }
     if (!strcmp(name, "exact_arithmetic")) { ctx->kopt.exact_window_sums = ctx->kopt.polyexp_exact = (value != 0); return OFB_OK; }
+    if (!strcmp(name, "fast_arithmetic")) { ctx->kopt.exact_window_sums = ctx->kopt.polyexp_exact = (value == 0); return OFB_OK; }
     if (!strcmp(name, "hsv_table")) { ctx->use_hsv_table = value != 0; return OFB_OK; }
     if (!strcmp(name, "batch")) { ctx->batch = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }
     if (!strcmp(name, "batch_scale0")) { ctx->batch0 = std::max(0, std::min(value, MAX_BATCH)); return OFB_OK; }

@@ -371,6 +371,19 @@ static void run_iter(Launch& L, IterArgs a, int batch)
 }
 
 
+// M is streamed (every element is used by one thread, once): under OFB_I64_NOALLOC its loads bypass L1 allocation so that the
+// small L1 left beside k_iter64's shared memory keeps the R1 lines the UpdateMatrices gathers re-use.
+__device__ __forceinline__ float ld_stream(const float* p)
+{
+#ifdef OFB_I64_NOALLOC
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_iter64<M, FUSE>: the box-window iteration with cv2's OWN arithmetic for the window sums and the solve (option
 // "exact_window_sums"): FarnebackUpdateFlow_Blur keeps, per column, ONE double running sum down the whole image,
@@ -420,7 +433,7 @@ k_iter64(IterArgs a)
     // old[r] = the row that LEAVES the window when it moves down to row ys + r:  max(ys + r - M - 1, 0)
     float old[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) old[i] = src[(size_t)min(max(ybeg - M - 1 + i, 0), H - 1) * pitch];
+    for (int i = 0; i < R; i++) old[i] = ld_stream(src + (size_t)min(max(ybeg - M - 1 + i, 0), H - 1) * pitch);
     // S = cv2's vsum BEFORE row ybeg is processed.  At the top of the image that is float(row0 * (m+2)) + rows 1..m-1;
     // a strip that starts lower (not used by the exact mode) starts from the plain sum of the window of row ybeg - 1.
     double S;
@@ -451,10 +464,10 @@ k_iter64(IterArgs a)
         if (ys + 3 * M < H) {
             const float* pb = src + (size_t)(ys + M) * pitch;
 #pragma unroll
-            for (int r = 0; r < R; r++) nb[r] = pb[r * pitch];
+            for (int r = 0; r < R; r++) nb[r] = ld_stream(pb + r * pitch);
         } else {
 #pragma unroll
-            for (int r = 0; r < R; r++) nb[r] = src[(size_t)min(ys + M + r, H - 1) * pitch];
+            for (int r = 0; r < R; r++) nb[r] = ld_stream(src + (size_t)min(ys + M + r, H - 1) * pitch);
         }
         if (a.prefetch && ys + R < yend) {
             const int yn = ys + R;

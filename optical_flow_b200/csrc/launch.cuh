@@ -61,8 +61,8 @@ struct KernelOptions {
     int generic_polyexp = 0;   // 1 = per-frame part (pyramid + polynomial expansion) through the simple kernels that keep cv2's exact float / double mix
     int pyr_fused = 1;         // scales 1..3 of the pyramid in one pass over the frame (k_pyr_fused)
     int polyexp_fast = 1;      // interior tiles of the polynomial expansion take pe_tile_fast (packed f32x2 vertical pass)
-    int polyexp_exact = 0;     // 1 = the horizontal pass of the polynomial expansion in cv2's exact float / double mix (bit-identical to the oracle)
-    int exact_window_sums = 0; // 1 = box-window sums with cv2's own arithmetic (k_iter64: double running sums of float differences down the
+    int polyexp_exact = 1;     // 1 = the horizontal pass of the polynomial expansion in cv2's exact float / double mix (bit-identical to the oracle)
+    int exact_window_sums = 1; // 1 = box-window sums with cv2's own arithmetic (k_iter64: double running sums of float differences down the
                                // whole column, double solve): matches cv2 where windows are rank-deficient; ~13 % slower per step
 };
 

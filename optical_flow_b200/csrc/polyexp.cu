@@ -612,7 +612,8 @@ __device__ __forceinline__ bool pe_tile_is_interior(const PolyArgs& a, int x0, i
 }
 
 template <int N, int SRC>
-__device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* pe_smem, const int x0, const int y0, const int z)
+__device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* pe_smem, const int x0, const int y0, const int z,
+                                             const bool exact)
 {
     using G = PeFast<N, SRC>;
     constexpr int TW = G::TW, TH = G::TH, RP = G::RP, HBP = G::HBP, RAWH = G::RAWH;
@@ -684,13 +685,27 @@ __device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* p
 #pragma unroll
         for (int o = 0; o < G::VROWS; o++) {
             const int cidx = o + N;
-            float2 r0 = pe_mul2(b[cidx], a.g[0]), r1 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);
+            float2 r0, r1 = make_float2(0.f, 0.f), r2 = make_float2(0.f, 0.f);
+            if (exact) {
+                // cv2's vertical pass (and pe_tile's): r = r + tap * (a +- b), multiply and add rounded separately
+                r0 = make_float2(__fmul_rn(b[cidx].x, a.g[0]), __fmul_rn(b[cidx].y, a.g[0]));
 #pragma unroll
-            for (int k = 1; k <= N; k++) {
-                const float2 sp = pe_add2(b[cidx - k], b[cidx + k]), sd = pe_sub2(b[cidx + k], b[cidx - k]);
-                r0 = pe_fma2(sp, a.g[k], r0);
-                r1 = pe_fma2(sd, a.xg[k], r1);
-                r2 = pe_fma2(sp, a.xxg[k], r2);
+                for (int k = 1; k <= N; k++) {
+                    const float2 lo = b[cidx - k], hi = b[cidx + k];
+                    const float px_ = __fadd_rn(lo.x, hi.x), py_ = __fadd_rn(lo.y, hi.y);
+                    r0.x = __fadd_rn(r0.x, __fmul_rn(a.g[k], px_)); r0.y = __fadd_rn(r0.y, __fmul_rn(a.g[k], py_));
+                    r1.x = __fadd_rn(r1.x, __fmul_rn(a.xg[k], __fsub_rn(hi.x, lo.x))); r1.y = __fadd_rn(r1.y, __fmul_rn(a.xg[k], __fsub_rn(hi.y, lo.y)));
+                    r2.x = __fadd_rn(r2.x, __fmul_rn(a.xxg[k], px_)); r2.y = __fadd_rn(r2.y, __fmul_rn(a.xxg[k], py_));
+                }
+            } else {
+                r0 = pe_mul2(b[cidx], a.g[0]);
+#pragma unroll
+                for (int k = 1; k <= N; k++) {
+                    const float2 sp = pe_add2(b[cidx - k], b[cidx + k]), sd = pe_sub2(b[cidx + k], b[cidx - k]);
+                    r0 = pe_fma2(sp, a.g[k], r0);
+                    r1 = pe_fma2(sd, a.xg[k], r1);
+                    r2 = pe_fma2(sp, a.xxg[k], r2);
+                }
             }
             const int e = (r0row + o) * RP + px;
             if (G::PO == 0) {
@@ -711,7 +726,51 @@ __device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* p
     const int gy = y0 + ly, gx0 = x0 + lx0;
     float o0[4], o1[4], o2[4], o3[4], o4[4];
     double c1[4];
-    {
+    if (exact) {
+        // cv2's float / double mix, as in pe_tile (the shared arrays hold the f32 vertical results widened exactly)
+        float w[4 + 2 * N];
+        const double2* q = reinterpret_cast<const double2*>(sR0 + ly * RP + lx0);
+#pragma unroll
+        for (int j = 0; j < (4 + 2 * N) / 2; j++) { const double2 t = q[j]; w[2 * j] = (float)t.x; w[2 * j + 1] = (float)t.y; }
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double b1 = (double)__fmul_rn(w[o + N], a.g[0]), b2 = 0, b4 = 0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                const double tg = (double)__fadd_rn(w[o + N + k], w[o + N - k]);
+                b1 = __dadd_rn(b1, __dmul_rn(tg, a.gd[k]));
+                b4 = __dadd_rn(b4, __dmul_rn(tg, a.xxgd[k]));
+                b2 = __dadd_rn(b2, (double)__fmul_rn(__fsub_rn(w[o + N + k], w[o + N - k]), a.xg[k]));
+            }
+            c1[o] = __dmul_rn(b1, a.ig03);
+            o1[o] = (float)__dmul_rn(b2, a.ig11);
+            o3[o] = (float)__dadd_rn(c1[o], __dmul_rn(b4, a.ig33));
+        }
+        q = reinterpret_cast<const double2*>(sR2 + ly * RP + lx0);
+#pragma unroll
+        for (int j = 0; j < (4 + 2 * N) / 2; j++) { const double2 t = q[j]; w[2 * j] = (float)t.x; w[2 * j + 1] = (float)t.y; }
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double b5 = (double)__fmul_rn(w[o + N], a.g[0]);
+#pragma unroll
+            for (int k = 1; k <= N; k++) b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(w[o + N + k], w[o + N - k]), a.g[k]));
+            o2[o] = (float)__dadd_rn(c1[o], __dmul_rn(b5, a.ig33));
+        }
+        q = reinterpret_cast<const double2*>(sR1 + ly * RP + lx0);
+#pragma unroll
+        for (int j = 0; j < (4 + 2 * N) / 2; j++) { const double2 t = q[j]; w[2 * j] = (float)t.x; w[2 * j + 1] = (float)t.y; }
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            double b3 = (double)__fmul_rn(w[o + N], a.g[0]), b6 = 0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) {
+                b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(w[o + N + k], w[o + N - k]), a.g[k]));
+                b6 = __dadd_rn(b6, (double)__fmul_rn(__fsub_rn(w[o + N + k], w[o + N - k]), a.xg[k]));
+            }
+            o0[o] = (float)__dmul_rn(b3, a.ig11);
+            o4[o] = (float)__dmul_rn(b6, a.ig55);
+        }
+    } else {
         double w[4 + 2 * N];
         const double2* q = reinterpret_cast<const double2*>(sR0 + ly * RP + lx0);
 #pragma unroll
@@ -768,12 +827,13 @@ k_polyexp2(PolyArgs a, int fast_path)
 {
     extern __shared__ __align__(128) unsigned char pe_smem[];
     const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH, z = blockIdx.z;
-    if (fast_path == 2) { pe_tile<N, SRC>(a, pe_smem, x0, y0, z, -1, true); return; }       // cv2's exact float / double mix, every tile
-    if (SRC != 2 && PE_TH == 16 && fast_path) {                  // block-uniform: interior tiles take the lean path
+    // fast_path: bit 0 = interior tiles take the lean pe_tile_fast, bit 1 = cv2's exact float / double arithmetic (every tile)
+    const bool exact = (fast_path & 2) != 0;
+    if (SRC != 2 && PE_TH == 16 && (fast_path & 1)) {            // block-uniform
         const unsigned char* srcb = (const unsigned char*)a.src + (size_t)z * a.src_item;
-        if (pe_tile_is_interior<N, SRC>(a, x0, y0, srcb)) { pe_tile_fast<N, SRC == 2 ? 0 : SRC>(a, pe_smem, x0, y0, z); return; }
+        if (pe_tile_is_interior<N, SRC>(a, x0, y0, srcb)) { pe_tile_fast<N, SRC == 2 ? 0 : SRC>(a, pe_smem, x0, y0, z, exact); return; }
     }
-    pe_tile<N, SRC>(a, pe_smem, x0, y0, z, -1);
+    pe_tile<N, SRC>(a, pe_smem, x0, y0, z, -1, exact);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -910,7 +970,7 @@ static void run_polyexp2(Launch& L, const PolyArgs& a, int batch)
     L.dyn_smem(k_polyexp2<N, SRC>, smem, configured);
     dim3 grid(divup(a.W, TW), divup(a.H, TH), batch);
     const char* nm = SRC == 0 ? "polyexp_level" : "polyexp_scale0";
-    const int fast_path = L.opt.polyexp_exact ? 2 : (L.opt.polyexp_fast && (SRC != 1 || ((a.W & 3) == 0 && (a.src_item & 3) == 0)) ? 1 : 0);
+    const int fast_path = (L.opt.polyexp_exact ? 2 : 0) | ((L.opt.polyexp_fast && (SRC != 1 || ((a.W & 3) == 0 && (a.src_item & 3) == 0))) ? 1 : 0);
     L.run(nm, [&](cudaStream_t s) { k_polyexp2<N, SRC><<<grid, PE_THREADS, smem, s>>>(a, fast_path); });
 }
 

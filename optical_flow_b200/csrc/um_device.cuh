@@ -28,8 +28,13 @@ __device__ __forceinline__ UmLoads um_load(int x, int y, float dx, float dy, con
     int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
     L.fx = fx - x1; L.fy = fy - y1;
     const unsigned o0 = (unsigned)y * (unsigned)R0.pitch + (unsigned)x;
+#ifdef OFB_R0_NOALLOC                   // R0 at the pixel itself is used once: keep it out of L1, which the R1 gathers re-use
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(L.q.x), "=f"(L.q.y), "=f"(L.q.z), "=f"(L.q.w) : "l"(R0.a + o0));
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(L.q4) : "l"(R0.b + o0));
+#else
     L.q = R0.a[o0];
     L.q4 = R0.b[o0];
+#endif
     L.inside = (unsigned)x1 < (unsigned)(W - 1) && (unsigned)y1 < (unsigned)(H - 1);
     if (L.inside) {
         const unsigned o1 = (unsigned)y1 * (unsigned)R1.pitch + (unsigned)x1;

@@ -42,21 +42,17 @@ def _textured(W, H, seed):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,sigma", [(5, 1.2), (7, 1.5), (3, 0.0)])
 def test_stage_polyexp_exact_mode_is_bit_identical_to_the_oracle(eng, oracle, n, sigma):
-    """Option "polyexp_exact": the batched kernel with cv2's own float / double mix in the horizontal pass (float sums and
+    """The default batched kernel (option polyexp_exact = 1) with cv2's own float / double mix in the horizontal pass (float sums and
     differences, four float products, separate double multiply and add) gives the oracle's R bit for bit."""
     f0, _ = _textured(203, 97, 2)
     img = oracle.gaussian_blur(f0.astype(np.float32), 3, 0.0)
-    eng.set_option("polyexp_exact", 1)
-    try:
-        got = eng.stage_polyexp(img, n, sigma)
-    finally:
-        eng.set_option("polyexp_exact", 0)
+    got = eng.stage_polyexp(img, n, sigma)               # polyexp_exact is the default
     assert np.array_equal(got, oracle.polyexp(img, n, sigma)), float(np.abs(got - oracle.polyexp(img, n, sigma)).max())
 
 
 @pytest.mark.parametrize("winsize", [3, 9, 15, 16, 33])
 def test_stage_blur_solve_exact_mode_follows_cv2_running_sums(eng, oracle, winsize):
-    """Option "exact_window_sums" (k_iter64): the oracle's flow to f32 rounding even on a matrix field whose windows are
+    """The default box-window kernel (k_iter64, option exact_window_sums = 1): the oracle's flow to f32 rounding even on a matrix field whose windows are
     exactly rank-deficient (one edge direction), where the default f32 sums differ visibly."""
     rng = np.random.default_rng(winsize)
     H, W = 150, 203
@@ -66,11 +62,7 @@ def test_stage_blur_solve_exact_mode_follows_cv2_running_sums(eng, oracle, winsi
     M[..., 0] = gx * gx; M[..., 3] = gx * 0.37
     M += rng.random((H, W, 5)).astype(np.float32) * 1e-3
     ref = oracle.blur_solve(M, winsize)
-    eng.set_option("exact_window_sums", 1)
-    try:
-        got = eng.stage_blur_solve(M, winsize)
-    finally:
-        eng.set_option("exact_window_sums", 0)
+    got = eng.stage_blur_solve(M, winsize)               # exact_window_sums is the default
     err = np.abs(got - ref).max()
     assert err <= 1e-5 * max(1.0, float(np.abs(ref).max())), (winsize, float(err))
 
@@ -89,18 +81,22 @@ def test_stage_level_image(eng, oracle, W, H, pyr, levels):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("generic", [0, 1, 2])
 @pytest.mark.parametrize("n,sigma", [(5, 1.2), (7, 1.5), (3, 0.0), (1, 1.2), (9, 2.0)])
 def test_stage_polyexp(eng, oracle, n, sigma, generic):
+    """generic 0 = default (cv2's mix, bit-exact), 1 = the simple kernels, 2 = option fast_arithmetic (f64-FMA horizontal pass,
+    FFMA2 vertical pass on interior tiles)."""
     f0, _ = _textured(203, 97, 2)
     img = oracle.gaussian_blur(f0.astype(np.float32), 3, 0.0)
     ref = oracle.polyexp(img, n, sigma)
-    eng.set_option("generic_kernels", generic)
+    eng.set_option("generic_kernels", 1 if generic == 1 else 0)
+    eng.set_option("fast_arithmetic", 1 if generic == 2 else 0)
     try:
         got = eng.stage_polyexp(img, n, sigma)
     finally:
         eng.set_option("generic_kernels", 0)
-    if generic or n not in (3, 5, 7):
+        eng.set_option("fast_arithmetic", 0)
+    if generic != 2 or n not in (3, 5, 7):
         # same expressions, same order, no contraction: bit-exact
         assert np.array_equal(got, ref), float(np.abs(got - ref).max())
     else:
@@ -125,9 +121,11 @@ def test_stage_update_matrices(eng, oracle, generic):
     assert np.array_equal(got, ref), float(np.abs(got - ref).max())
 
 
-@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("generic", [0, 1, 2])
 @pytest.mark.parametrize("winsize", [15, 9, 31, 16, 3, 2, 1, 33, 41])
 def test_stage_blur_solve_box(eng, oracle, winsize, generic):
+    """generic 0 = the default kernel (k_iter64: cv2's double running sums), 1 = the simple global-memory kernels,
+    2 = option fast_arithmetic (k_iter: f32 van Herk sums, compensated f32 solve)."""
     rng = np.random.default_rng(4)
     H, W = 143, 211
     r = rng.normal(0, 3, (H, W, 5)).astype(np.float32)
@@ -138,15 +136,17 @@ def test_stage_blur_solve_box(eng, oracle, winsize, generic):
     M[..., 3] = r[..., 3]
     M[..., 4] = r[..., 4]
     ref = oracle.blur_solve(M, winsize, gaussian=False)
-    eng.set_option("generic_kernels", generic)
+    eng.set_option("generic_kernels", 1 if generic == 1 else 0)
+    eng.set_option("fast_arithmetic", 1 if generic == 2 else 0)
     try:
         got = eng.stage_blur_solve(M, winsize, gaussian=False)
     finally:
         eng.set_option("generic_kernels", 0)
+        eng.set_option("fast_arithmetic", 0)
     mean, mx = epe(got, ref)
     scale = max(1.0, float(np.abs(ref).max()))
-    # generic: f64 direct sums.  fast path: f32 van Herk window sums + Kahan-compensated f32 solve.
-    tol = 2e-5 if generic else 2e-4
+    # default / generic: f64 sums.  fast_arithmetic: f32 van Herk window sums + Kahan-compensated f32 solve.
+    tol = 2e-4 if generic == 2 else 2e-5
     print("blur_solve box win %d generic %d: max diff %.2e (|flow| max %.2f)" % (winsize, generic, mx, scale))
     assert mx <= tol * scale, (winsize, mean, mx, scale)
 
@@ -621,14 +621,16 @@ def test_polyexp_tma_path_is_bit_identical(eng):
     default kernel (same arithmetic; only where the raw patch comes from differs), on a frame with interior and border tiles."""
     f = _textured(448, 200, 5)[0]
     frames = np.stack([np.roll(f, (i, 2 * i), (0, 1)) for i in range(4)])
-    eng.set_option("polyexp_fast", 0)                 # the TMA kernel runs pe_tile's arithmetic (interior tiles of the default path
-    try:                                              # use FFMA2 in the vertical pass, <= 1 ulp away)
+    eng.set_option("fast_arithmetic", 1)              # the TMA kernel is a variant of the fast-arithmetic path
+    eng.set_option("polyexp_fast", 0)                 # ... with pe_tile's arithmetic (pe_tile_fast uses FFMA2 in the vertical pass)
+    try:
         ref = eng.shot(frames, want_bgr=True, want_flow=True)
         eng.set_option("polyexp_tma", 1)
         got = eng.shot(frames, want_bgr=True, want_flow=True)
     finally:
         eng.set_option("polyexp_tma", 0)
         eng.set_option("polyexp_fast", 1)
+        eng.set_option("fast_arithmetic", 0)
     assert np.array_equal(got["flow"], ref["flow"])
     assert np.array_equal(got["bgr"], ref["bgr"])
 

@@ -12,6 +12,7 @@ tb = importlib.util.module_from_spec(spec); spec.loader.exec_module(tb)
 from oracle import c_oracle
 c_oracle.build()
 eng = ofb.Farneback(0)
+eng.set_option("fast_arithmetic", 1)          # the options below are switched on one at a time from the fast baseline
 for kind, ws in (("high_contrast_checker", 15), ("high_contrast_checker", 33), ("flat_field_moving_square", 15), ("step_edges", 15)):
     f0, f1 = tb._stress_frames(kind)
     kw = dict(tb.REF, winsize=ws)

@@ -15,6 +15,7 @@ import re
 FAMILY = [(r"k_polyexp2<\d+, [12]>", "polyexp_scale0"), (r"k_polyexp2<", "polyexp_level"), (r"k_pyr_vf<", "pyr_v_u8"),
           (r"k_pyr_hf<", "pyr_h"), (r"k_pyr_h", "pyr_h_u8"), (r"k_pyr_v", "pyr_v"), (r"k_um0<0>", "um0_zero"),
           (r"k_um0<2>", "um0_upsample"), (r"k_um0<1>", "um0_flow"),
+          (r"k_iter64<\d+, 1>", "iter_fused"), (r"k_iter64<\d+, 0>", "iter_last"), (r"k_pyr_fused", "pyr_fused"),
           (r"k_iter<\d+, 1, \d+, 0>", "iter_fused"), (r"k_iter<\d+, 0, \d+, 0>", "iter_last"),
           (r"k_iter<\d+, 1, \d+, 1>", "iter_fused_gauss"), (r"k_iter<\d+, 0, \d+, 1>", "iter_last_gauss"),
           (r"k_flow_to_bgr", "flow_to_bgr_v4"), (r"k_minmax_reset", "minmax_reset"), (r"k_minmax", "minmax_mag"),
