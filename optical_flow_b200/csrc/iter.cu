@@ -404,18 +404,35 @@ __device__ __forceinline__ float ld_stream(const float* p)
 // UpdateMatrices exactly as in k_iter.  Shared memory: 8 * 5R * (97 + TW + 1) bytes = 108 KB for winsize 15, two CTAs per SM.
 // Measured on B200 against k_iter: iter_fused +26 %, iter_last +42 % (f64 shared-memory traffic), whole step -13 %.
 // ------------------------------------------------------------------------------------------------
+// Tile width of k_iter64 (columns loaded per CTA; 5 channels x I64_CW threads).  Measured on B200, 1080p, ms per 300-pair step
+// (iter_fused / iter_last): see DESIGN.md section 4d.
+#ifndef OFB_I64_CW
+#define OFB_I64_CW 96
+#endif
+constexpr int I64_CW = OFB_I64_CW, I64_THREADS = 5 * I64_CW, I64_VP = I64_CW + 1;
+constexpr int i64_min_blocks(int M)
+{
+    // CTAs per SM that shared memory (227 KB) and the register file (64 K / threads, <= 64 registers each... the cap the bound sets) allow
+    const int R = 2 * M + 1, TW = I64_CW - 2 * M;
+    const long smem = 8L * 5 * R * (I64_VP + TW + 1) + 1024;
+    int by_smem = (int)(232448L / smem);
+    int by_regs = 65536 / (I64_THREADS * 64);
+    int n = by_smem < by_regs ? by_smem : by_regs;
+    return n < 1 ? 1 : (n > 3 ? 3 : n);
+}
+
 template <int M, bool FUSE>
-__global__ void __launch_bounds__(IT_THREADS, (M <= 7) ? 2 : 1)
+__global__ void __launch_bounds__(I64_THREADS, i64_min_blocks(M))
 k_iter64(IterArgs a)
 {
     constexpr int R = 2 * M + 1;
-    constexpr int TW = IT_CW - 2 * M;
+    constexpr int TW = I64_CW - 2 * M;
     constexpr int HP = TW + 1;
     constexpr int NSEG = (TW + R - 1) / R;
-    static_assert(TW >= 1 && 5 * R * NSEG <= IT_THREADS, "H phase: one thread per (channel, row, segment)");
+    static_assert(TW >= 1 && 5 * R * NSEG <= I64_THREADS, "H phase: one thread per (channel, row, segment)");
     extern __shared__ double it_smem64[];
-    double* sV = it_smem64;                     // 5 * R * IT_VP
-    double* sH = it_smem64 + 5 * R * IT_VP;     // 5 * R * HP
+    double* sV = it_smem64;                     // 5 * R * I64_VP
+    double* sH = it_smem64 + 5 * R * I64_VP;     // 5 * R * HP
 
     const int tid = threadIdx.x;
     const int z = blockIdx.x, bx = blockIdx.y, bs = blockIdx.z;
@@ -425,7 +442,7 @@ k_iter64(IterArgs a)
     const int yend = min(ybeg + a.strip_rows, H);
     if (ybeg >= H) return;
 
-    const int vc = tid / IT_CW, vcol = tid - vc * IT_CW;
+    const int vc = tid / I64_CW, vcol = tid - vc * I64_CW;
     const int gx = min(max(x0 - M + vcol, 0), W - 1);                 // replicate border in x
     const float* __restrict__ src = a.Min + (size_t)z * a.m_item + (size_t)vc * a.plane + gx;
     const int pitch = a.pitch;
@@ -500,11 +517,11 @@ k_iter64(IterArgs a)
             }
         }
         {
-            double* v = sV + vc * R * IT_VP + vcol;
+            double* v = sV + vc * R * I64_VP + vcol;
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 S += (double)__fsub_rn(nb[r], old[r]);                 // cv2: vsum[x] += srow1[x] - srow0[x]  (float difference)
-                v[r * IT_VP] = S;                                      // window of row ys + r
+                v[r * I64_VP] = S;                                      // window of row ys + r
                 old[r] = nb[r];                                        // the rows that entered now leave during the next step
             }
         }
@@ -514,11 +531,11 @@ k_iter64(IterArgs a)
         if (tid < 5 * R * NSEG) {
             const int seg = tid / (5 * R), rc = tid - seg * (5 * R);
             const int xa = seg * R;
-            const double* v = sV + rc * IT_VP + xa;
+            const double* v = sV + rc * I64_VP + xa;
             double* h = sH + rc * HP + xa;
             double sa[R];
 #pragma unroll
-            for (int i = 0; i < R; i++) sa[i] = (xa + i < IT_CW) ? v[i] : 0.0;
+            for (int i = 0; i < R; i++) sa[i] = (xa + i < I64_CW) ? v[i] : 0.0;
 #pragma unroll
             for (int i = R - 2; i >= 0; i--) sa[i] = sa[i] + sa[i + 1];
             if (xa < TW) h[0] = sa[0];
@@ -535,7 +552,7 @@ k_iter64(IterArgs a)
         __syncthreads();
 
         // ---- S phase: item = pixel ----
-        for (int i = tid; i < R * TW; i += IT_THREADS) {
+        for (int i = tid; i < R * TW; i += I64_THREADS) {
             const int r = i / TW, lx = i - r * TW;
             const int y = ys + r, x = x0 + lx;
             if (y < yend && x < W) {
@@ -582,15 +599,15 @@ k_iter64(IterArgs a)
 template <int M, bool FUSE>
 static void run_iter64(Launch& L, IterArgs a, int batch)
 {
-    constexpr int R = 2 * M + 1, TW = IT_CW - 2 * M, HP = TW + 1;
-    const size_t smem = sizeof(double) * (5 * R * IT_VP + 5 * R * HP);
+    constexpr int R = 2 * M + 1, TW = I64_CW - 2 * M, HP = TW + 1;
+    const size_t smem = sizeof(double) * (5 * R * I64_VP + 5 * R * HP);
     static unsigned long long configured = 0;
     L.dyn_smem(k_iter64<M, FUSE>, smem, configured);
     const int xt = divup(a.W, TW);
     a.strip_rows = divup(a.H, R) * R;                        // ONE strip: cv2's running sums (and their drift) run down the whole column
     a.prefetch = L.opt.iter_prefetch;
     dim3 grid(batch, xt, 1);
-    L.run(FUSE ? "iter_fused" : "iter_last", [&](cudaStream_t s) { k_iter64<M, FUSE><<<grid, IT_THREADS, smem, s>>>(a); });
+    L.run(FUSE ? "iter_fused" : "iter_last", [&](cudaStream_t s) { k_iter64<M, FUSE><<<grid, I64_THREADS, smem, s>>>(a); });
 }
 
 bool iter_supported(int winsize) { int m = winsize / 2; return m >= 1 && m <= 16; }
