@@ -20,7 +20,8 @@ The default line (workload "shot"), rank 0:
   legs             the same shot with other deliveries of the result: "jpeg" (the reference's artefact,
                    visualize_optical_flow.py:57-58: the picture leaves the GPU as a baseline JPEG byte stream) and "feature"
                    (optical_flow.py:61-64: one float per pair); "rough_motion": the raw-picture protocol on 10-20 px
-                   piecewise-constant motion instead of the smooth 2.5 px affine.
+                   piecewise-constant motion instead of the smooth 2.5 px affine; "fast_arithmetic": the raw-picture protocol
+                   with round 1's f32 window sums instead of the default cv2-exact arithmetic.
   parity           after the timing: pairs at every kind of schedule seam compared with cv2 itself.
   roofline         per-kernel CUDA-event durations (option "profile") of one extra pass; the dominant kernel's
                    algorithmic bytes per launch / its average duration, against MEASURED_PEAKS.json.

@@ -91,3 +91,23 @@ def test_shot_jpeg_1080p_default_batch(eng):
         stream = res["jpeg"][res["offsets"][t]:res["offsets"][t] + res["sizes"][t]]
         assert np.array_equal(stream, cv2.imencode(".jpeg", raw[t])[1].ravel()), t
     print("1080p JPEG streams: mean %.0f bytes (raw picture %d bytes)" % (res["sizes"].mean(), raw[0].nbytes))
+
+
+def test_frame_list_and_bgr_entry_points_deliver_the_same_files(eng):
+    """ofb_shot_host_v / ofb_shot_host_v_jpeg (frames in a decoder's own buffers) and ofb_shot_bgr_host_jpeg (decoded BGR frames in)
+    against the contiguous gray entry points: same pictures, same JPEG bytes."""
+    cv2 = pytest.importorskip("cv2")
+    import synth_frames
+    frames = synth_frames.shot(320, 184, 7, seed=9)
+    flist = [np.ascontiguousarray(f) for f in frames]
+    a = eng.shot(frames, want_bgr=True, want_magsum=True)
+    b = eng.shot_frames(flist, want_bgr=True, want_magsum=True)
+    assert np.array_equal(a["bgr"], b["bgr"]) and np.array_equal(a["magsum"], b["magsum"])
+    ja, jb = eng.shot_jpeg(frames), eng.shot_frames_jpeg(flist)
+    assert np.array_equal(ja["sizes"], jb["sizes"])
+    n = int(ja["sizes"].sum())
+    assert np.array_equal(ja["jpeg"][:n], jb["jpeg"][:n])
+    bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in frames])      # B = G = R: the gray conversion gives the frame back
+    jc = eng.shot_bgr_jpeg(bgr)
+    for t in range(6):
+        assert np.array_equal(jc["files"][t], cv2.imencode(".jpeg", a["bgr"][t])[1].ravel()), t

@@ -756,3 +756,46 @@ def test_repeated_runs_are_bitwise_identical(eng):
         if ref is None:
             ref = cur
         assert cur == ref, rep
+
+
+def test_cart_to_polar_in_degrees_and_in_place_outputs(eng):
+    """cv2.cartToPolar(x, y, angleInDegrees=True) and the optional magnitude / angle destinations (boundary nits of round 1)."""
+    cv2 = _cv2_or_none()
+    import optical_flow_b200 as ofb
+    rng = np.random.default_rng(2)
+    x = rng.normal(0, 3, (37, 53)).astype(np.float32)
+    y = rng.normal(0, 3, (37, 53)).astype(np.float32)
+    mag, ang = ofb.cartToPolar(x, y, angleInDegrees=True)
+    m2, a2 = ofb.cartToPolar(x, y)
+    assert np.array_equal(mag, m2)
+    assert np.allclose(ang, np.degrees(a2), rtol=0, atol=1e-4)
+    dst_m, dst_a = np.empty_like(x), np.empty_like(x)
+    rm, ra = ofb.cartToPolar(x, y, dst_m, dst_a)
+    assert rm is dst_m and ra is dst_a and np.array_equal(dst_m, m2) and np.array_equal(dst_a, a2)
+    if cv2 is not None:
+        cm, ca = cv2.cartToPolar(x, y, angleInDegrees=True)
+        assert np.array_equal(mag, cm) and np.array_equal(ang, ca)
+        try:
+            ofb.calcOpticalFlowFarneback(np.zeros((8, 8), np.uint8), np.zeros((8, 9), np.uint8), None, 0.5, 3, 15, 3, 5, 1.2, 0)
+            assert False, "size mismatch must raise"
+        except cv2.error as e:                     # ofb.error IS a cv2.error
+            assert "prev0.size() == next0.size()" in str(e)
+
+
+def test_two_devices_in_one_process():
+    """Function attributes (dynamic shared memory above 48 KB) and kernel options are per device / per context: a second engine
+    on another GPU of the same process must work and give the same bits (round-1 advisor finding).  Needs two GPUs."""
+    import optical_flow_b200 as ofb
+    from optical_flow_b200 import _lib
+    if _lib.load().ofb_device_count() < 2:
+        pytest.skip("one GPU visible")
+    f0, f1 = _textured(448, 200, 3)
+    kw = dict(ofb.REFERENCE_PARAMS)
+    e0, e1 = ofb.Farneback(0), ofb.Farneback(1)
+    e1.set_option("fast_arithmetic", 1)                      # options do not leak between contexts
+    a = e0.pair(f0, f1, want_bgr=True, want_flow=True, **kw)
+    e1.set_option("fast_arithmetic", 0)
+    b = e1.pair(f0, f1, want_bgr=True, want_flow=True, **dict(kw, poly_n=7, poly_sigma=1.5))      # another kernel instance first
+    b = e1.pair(f0, f1, want_bgr=True, want_flow=True, **kw)
+    assert np.array_equal(a["flow"], b["flow"]) and np.array_equal(a["bgr"], b["bgr"])
+    assert e0.check_guards() == 0 and e1.check_guards() == 0

@@ -174,3 +174,15 @@ def test_jpeg_writer_writes_the_same_bytes_as_imwrite(tmp_path):
     for i, im in enumerate(imgs):
         cv2.imwrite(str(tmp_path / ("b%d.jpeg" % i)), im)
         assert (tmp_path / ("a%d.jpeg" % i)).read_bytes() == (tmp_path / ("b%d.jpeg" % i)).read_bytes()
+
+
+def test_error_is_a_cv2_error_and_argument_errors_need_no_gpu():
+    """ofb.error subclasses the installed cv2.error (so `except cv2.error` keeps working); the argument contract of
+    calcOpticalFlowFarneback is checked on the host before any GPU call."""
+    cv2 = pytest.importorskip("cv2")
+    from optical_flow_b200.engine import validate_call, error
+    assert issubclass(error, cv2.error)
+    with pytest.raises(cv2.error):
+        validate_call(np.zeros((8, 8), np.uint8), np.zeros((8, 9), np.uint8), None, 0.5, 0)
+    with pytest.raises(cv2.error):
+        validate_call(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.uint8), None, 1.0, 0)
