@@ -444,8 +444,10 @@ def run_shot(args, rank, local_rank, world):
     kernels = {}
     if rank == 0:
         eng.set_option("profile", 1)
+        eng.set_option("overlap_expand", 0)         # one stream: every kernel alone on the GPU, so its events time that kernel
         eng.reset_kernel_stats()
         eng.shot_device(d_frames, P + 1, W, H, d_bgr=d_bgr, **PARAMS)
+        eng.set_option("overlap_expand", 1)
         stats = eng.kernel_stats()
         if "jpeg" in legs:                          # the encoder's own kernels: CUDA events around each, one 48-pair pass
             eng.reset_kernel_stats()

@@ -89,7 +89,9 @@ struct Plan {
 struct ofb_context {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr, s_expand = nullptr;
+    cudaEvent_t ev_expanded[2]{}, ev_solved[2]{};
+    bool overlap_expand = true;         // per-frame work of chunk c+1 on s_expand while the per-pair work of chunk c runs on s_compute
     cudaEvent_t ev_h2d[2]{}, ev_frame_free[2]{}, ev_out_ready[2]{}, ev_out_free[2]{}, ev_t0 = nullptr, ev_t1 = nullptr;
     std::string err;
     Profiler prof;
@@ -148,7 +150,7 @@ struct DrainOnError {
     ~DrainOnError()
     {
         if (!armed) return;
-        cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_compute); cudaStreamSynchronize(c->s_d2h);
+        cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_expand); cudaStreamSynchronize(c->s_compute); cudaStreamSynchronize(c->s_d2h);
         cudaGetLastError();
     }
 };
@@ -330,10 +332,12 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
     batch = std::max(1, std::min(batch, MAX_BATCH));
     if (pl.valid && pl.W == W && pl.H == H && pl.dtype == dtype && same_params(pl.p, *p) && pl.batch >= batch) return 0;
     CU(cudaStreamSynchronize(ctx->s_compute));
+    CU(cudaStreamSynchronize(ctx->s_expand));
     CU(cudaStreamSynchronize(ctx->s_h2d));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     free_plan(pl);
-    pl.W = W; pl.H = H; pl.dtype = dtype; pl.p = *p; pl.batch = batch; pl.nslots = 2 * batch;
+    pl.W = W; pl.H = H; pl.dtype = dtype; pl.p = *p; pl.batch = batch;
+    pl.nslots = 2 * batch + 1;          // a chunk's b+1 frames stay readable while the next chunk's b frames are being expanded
     pl.K = num_scales(W, H, p->pyr_scale, p->levels);
     pl.lv.resize(pl.K + 1);
     const size_t B = (size_t)batch;
@@ -762,11 +766,14 @@ int ofb_create(int device, ofb_context** out)
     ok(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&c->s_expand, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         ok(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&c->ev_frame_free[i], cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&c->ev_out_ready[i], cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&c->ev_out_free[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&c->ev_expanded[i], cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&c->ev_solved[i], cudaEventDisableTiming));
     }
     ok(cudaEventCreate(&c->ev_t0));
     ok(cudaEventCreate(&c->ev_t1));
@@ -810,9 +817,10 @@ void ofb_destroy(ofb_context* ctx)
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_frame_free[i]);
         cudaEventDestroy(ctx->ev_out_ready[i]); cudaEventDestroy(ctx->ev_out_free[i]);
+        cudaEventDestroy(ctx->ev_expanded[i]); cudaEventDestroy(ctx->ev_solved[i]);
     }
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
-    cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+    cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); cudaStreamDestroy(ctx->s_expand);
     delete ctx;
 }
 
@@ -825,6 +833,7 @@ int ofb_synchronize(ofb_context* ctx)
     if (!ctx) return OFB_ERR_BAD_ARG;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->s_h2d));
+    CU(cudaStreamSynchronize(ctx->s_expand));
     CU(cudaStreamSynchronize(ctx->s_compute));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     return OFB_OK;
@@ -1031,19 +1040,38 @@ int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int
     cudaStream_t s = ctx->s_compute;
     const size_t n = (size_t)W * H;
     Launch L = make_launch(ctx, s);
+    cudaStream_t se = ctx->overlap_expand ? ctx->s_expand : s;
+    Launch LE = make_launch(ctx, se);
     CU(cudaEventRecord(ctx->ev_t0, s));
-    expand_frames(ctx, L, d_frames, n, (size_t)W, 0, 1);
-    for (int t0 = 0; t0 + 1 < n_frames; t0 += B) {
-        const int b = std::min(B, n_frames - 1 - t0);
-        expand_frames(ctx, L, d_frames + (size_t)(t0 + 1) * n, n, (size_t)W, t0 + 1, b);
+    if (se != s) CU(cudaStreamWaitEvent(se, ctx->ev_t0, 0));
+    // chunk c+1 is expanded on `se` while the pairs of chunk c are solved on `s` (ring of 2 * batch + 1 frame slots)
+    auto expand_chunk = [&](int c) -> int {
+        const int t0 = c * B, b = std::min(B, n_frames - 1 - t0), par = c & 1;
+        if (se != s && c >= 2) CU(cudaStreamWaitEvent(se, ctx->ev_solved[par], 0));
+        if (c == 0) expand_frames(ctx, LE, d_frames, n, (size_t)W, 0, 1);
+        expand_frames(ctx, LE, d_frames + (size_t)(t0 + 1) * n, n, (size_t)W, t0 + 1, b);
+        if (se != s) CU(cudaEventRecord(ctx->ev_expanded[par], se));
+        return 0;
+    };
+    const int n_chunks = (n_frames - 1 + B - 1) / B;
+    if (int rc = expand_chunk(0)) return rc;
+    for (int c = 0; c < n_chunks; c++) {
+        const int t0 = c * B, b = std::min(B, n_frames - 1 - t0), par = c & 1;
+        if (se != s) {
+            CU(cudaStreamWaitEvent(s, ctx->ev_expanded[par], 0));
+            if (c + 1 < n_chunks) if (int rc = expand_chunk(c + 1)) return rc;
+        }
         float2* fl = d_flow ? (float2*)d_flow + (size_t)t0 * n : pl.flow0[0];
         const bool mm = solve_pairs(ctx, L, t0, b, fl, n, 1, d_bgr != nullptr);
         if (d_bgr) picture(ctx, L, fl, n, n, d_bgr + (size_t)t0 * n * 3, n * 3, b, mm);
         if (d_magsum) launch_sum_magnitude_batch(L, fl, n, n, ctx->sumacc, d_magsum + t0, b);
+        CU(cudaEventRecord(ctx->ev_solved[par], s));
+        if (se == s && c + 1 < n_chunks) if (int rc = expand_chunk(c + 1)) return rc;
     }
     CU(cudaEventRecord(ctx->ev_t1, s));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
+    CU(cudaStreamSynchronize(se));
     if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
     return OFB_OK;
 }
@@ -1141,26 +1169,35 @@ static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next
     for (int c = 0; c < n_chunks; c++) {
         const int t0 = cstart[c], b = cstart[c + 1] - t0, par = c & 1;
         if (c + 1 < n_chunks) if (int rc = upload(c + 1)) return rc;
-        CU(cudaStreamWaitEvent(sc, ctx->ev_h2d[par], 0));
+        // Per-frame work of this chunk on `se`: with overlap (shot mode) that is s_expand, so it runs beside the per-pair kernels of
+        // the PREVIOUS chunk on s_compute; its ring slots were last read by the chunk two back (nslots = 2 * batch + 1).
+        cudaStream_t se = (ctx->overlap_expand && !pairs) ? ctx->s_expand : sc;
+        Launch LE = make_launch(ctx, se);
+        CU(cudaStreamWaitEvent(se, ctx->ev_h2d[par], 0));
+        if (se != sc && c >= 2) CU(cudaStreamWaitEvent(se, ctx->ev_solved[par], 0));
         uint8_t* g_lo = pl.fstage[par];
         uint8_t* g_hi = pl.fstage[par] + n * B;
         if (from_bgr) {
-            if (!pairs && c == 0) preprocess_frames(ctx, L, bs0, sn, sW, sH, pl.f0, n, W, H, 1);
-            preprocess_frames(ctx, L, bs[par], sn, sW, sH, g_lo, n, W, H, b);
-            if (pairs) preprocess_frames(ctx, L, bs[par] + sna * B, sn, sW, sH, g_hi, n, W, H, b);
+            if (!pairs && c == 0) preprocess_frames(ctx, LE, bs0, sn, sW, sH, pl.f0, n, W, H, 1);
+            preprocess_frames(ctx, LE, bs[par], sn, sW, sH, g_lo, n, W, H, b);
+            if (pairs) preprocess_frames(ctx, LE, bs[par] + sna * B, sn, sW, sH, g_hi, n, W, H, b);
             if (gray_out && !pairs) {   // the gray frames the reference would have computed on the host (stream-ordered copy)
-                if (c == 0) CU(cudaMemcpyAsync(gray_out, pl.f0, n, cudaMemcpyDeviceToHost, sc));
-                CU(cudaMemcpyAsync(gray_out + (size_t)(t0 + 1) * n, g_lo, (size_t)b * n, cudaMemcpyDeviceToHost, sc));
+                if (c == 0) CU(cudaMemcpyAsync(gray_out, pl.f0, n, cudaMemcpyDeviceToHost, se));
+                CU(cudaMemcpyAsync(gray_out + (size_t)(t0 + 1) * n, g_lo, (size_t)b * n, cudaMemcpyDeviceToHost, se));
             }
         }
         if (pairs) {
-            expand_frames(ctx, L, g_lo, n, (size_t)W, 0, b, 2);           // prev[z] -> slot 2z
-            expand_frames(ctx, L, g_hi, n, (size_t)W, 1, b, 2);           // next[z] -> slot 2z+1
+            expand_frames(ctx, LE, g_lo, n, (size_t)W, 0, b, 2);          // prev[z] -> slot 2z
+            expand_frames(ctx, LE, g_hi, n, (size_t)W, 1, b, 2);          // next[z] -> slot 2z+1
         } else {
-            if (c == 0) expand_frames(ctx, L, pl.f0, n, (size_t)W, 0, 1);
-            expand_frames(ctx, L, g_lo, n, (size_t)W, t0 + 1, b);
+            if (c == 0) expand_frames(ctx, LE, pl.f0, n, (size_t)W, 0, 1);
+            expand_frames(ctx, LE, g_lo, n, (size_t)W, t0 + 1, b);
         }
-        CU(cudaEventRecord(ctx->ev_frame_free[par], sc));
+        CU(cudaEventRecord(ctx->ev_frame_free[par], se));
+        if (se != sc) {
+            CU(cudaEventRecord(ctx->ev_expanded[par], se));
+            CU(cudaStreamWaitEvent(sc, ctx->ev_expanded[par], 0));
+        }
         if (c >= 2) CU(cudaStreamWaitEvent(sc, ctx->ev_out_free[par], 0));
         const bool want_pic = bgr != nullptr || want_jpeg;
         const bool mm = pairs ? solve_pairs(ctx, L, 0, b, pl.flow0[par], n, 2, want_pic)
@@ -1169,6 +1206,7 @@ static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next
         if (want_jpeg) launch_jpeg_encode(L, ctx->jw, pl.bgr[par], n * 3, b, ctx->jout[par], d_jsizes + t0, ctx->d_tot[par]);
         if (magsum) launch_sum_magnitude_batch(L, pl.flow0[par], n, n, ctx->sumacc, d_sums + t0, b);
         CU(cudaEventRecord(ctx->ev_out_ready[par], sc));
+        CU(cudaEventRecord(ctx->ev_solved[par], sc));
         if (bgr || flow || want_jpeg) {
             if (!want_jpeg || bgr || flow) CU(cudaStreamWaitEvent(sd, ctx->ev_out_ready[par], 0));
             if (bgr) CU(cudaMemcpyAsync(bgr + (size_t)t0 * n * 3, pl.bgr[par], (size_t)b * n * 3, cudaMemcpyDeviceToHost, sd));
@@ -1197,6 +1235,7 @@ static int host_impl(ofb_context* ctx, const uint8_t* first, const uint8_t* next
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(sd));
     CU(cudaStreamSynchronize(sc));
+    CU(cudaStreamSynchronize(ctx->s_expand));
     CU(cudaStreamSynchronize(su));
     drain.armed = false;
     if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev_t0, ctx->ev_t1));
@@ -1582,6 +1621,7 @@ int ofb_set_option(ofb_context* ctx, const char* name, int value)
     if (!strcmp(name, "iter_ilp")) { ctx->kopt.iter_ilp = value; return OFB_OK; }
     if (!strcmp(name, "iter_prefetch")) { ctx->kopt.iter_prefetch = value; return OFB_OK; }
     if (!strcmp(name, "polyexp_tma")) { ctx->kopt.polyexp_tma = value; return OFB_OK; }
+    if (!strcmp(name, "overlap_expand")) { ctx->overlap_expand = value != 0; return OFB_OK; }
     if (!strcmp(name, "generic_polyexp")) { ctx->kopt.generic_polyexp = value; return OFB_OK; }
     if (!strcmp(name, "pyr_fused")) { ctx->kopt.pyr_fused = value; return OFB_OK; }
     if (!strcmp(name, "polyexp_fast")) { ctx->kopt.polyexp_fast = value; return OFB_OK; }

@@ -768,7 +768,7 @@ def test_cart_to_polar_in_degrees_and_in_place_outputs(eng):
     mag, ang = ofb.cartToPolar(x, y, angleInDegrees=True)
     m2, a2 = ofb.cartToPolar(x, y)
     assert np.array_equal(mag, m2)
-    assert np.allclose(ang, np.degrees(a2), rtol=0, atol=1e-4)
+    assert np.allclose(ang, np.degrees(a2.astype(np.float64)), rtol=1e-5, atol=1e-4)          # radians = degrees * (pi/180) in f32
     dst_m, dst_a = np.empty_like(x), np.empty_like(x)
     rm, ra = ofb.cartToPolar(x, y, dst_m, dst_a)
     assert rm is dst_m and ra is dst_a and np.array_equal(dst_m, m2) and np.array_equal(dst_a, a2)
