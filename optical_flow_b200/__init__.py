@@ -52,11 +52,12 @@ def cartToPolar(x, y, magnitude=None, angle=None, angleInDegrees=False):
     shp = x.shape
     fl = np.stack([x.reshape(-1), y.reshape(-1)], -1).reshape(1, -1, 2)
     mag, ang = default_engine().cart_to_polar(fl, angle_in_degrees=bool(angleInDegrees))
+    mag, ang = mag.reshape(shp), ang.reshape(shp)
     if magnitude is not None and isinstance(magnitude, np.ndarray) and magnitude.shape == shp and magnitude.dtype == np.float32:
-        magnitude[...] = mag.reshape(shp); mag = magnitude           # cv2 fills a correctly typed destination in place
+        magnitude[...] = mag; mag = magnitude           # cv2 fills a correctly typed destination in place
     if angle is not None and isinstance(angle, np.ndarray) and angle.shape == shp and angle.dtype == np.float32:
-        angle[...] = ang.reshape(shp); ang = angle
-    return mag.reshape(shp), ang.reshape(shp)
+        angle[...] = ang; ang = angle
+    return mag, ang
 
 
 def flow_to_bgr(flow):
