@@ -122,11 +122,13 @@ __device__ __forceinline__ float u8_to_f32(unsigned int b) { return __uint_as_fl
 template <typename T> __device__ __forceinline__ float px_to_f32(T v) { return (float)v; }
 template <> __device__ __forceinline__ float px_to_f32<unsigned char>(unsigned char v) { return u8_to_f32(v); }
 
-// Source coordinate of cv::resize(INTER_LINEAR), evaluated in double like the
-// installed wheel does: returns the left/top sample index, writes the f32 weight of the next one.
-__device__ inline int linear_coord(int d, double scale, int src_len, float* w1)
+// Source coordinate of cv::resize(INTER_LINEAR): returns the left/top sample index, writes the f32 weight of
+// the next one.  f32_coord = false: coordinate kept in double (cv2's one-channel f32 resize, the level images); true: rounded
+// to f32 before the floor (cv2's generic path, which the two-channel flow up-sample takes) -- see linear_table in engine.cu.
+__device__ inline int linear_coord(int d, double scale, int src_len, float* w1, bool f32_coord = false)
 {
     double f = (d + 0.5) * scale - 0.5;
+    if (f32_coord) f = (double)(float)f;
     int s = (int)floor(f);
     f -= s;
     if (s < 0) { s = 0; f = 0; }

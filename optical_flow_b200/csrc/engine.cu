@@ -249,13 +249,18 @@ void gauss_half_taps(int winsize, std::vector<float>& k)
     for (int i = 0; i <= m; i++) k[i] = (float)(k[i] * s);
 }
 
-// cv::resize(INTER_LINEAR) coordinate rule, double-precision coordinates
-void linear_table(int dst, int src, std::vector<int>& idx, std::vector<float>& w1)
+// cv::resize(INTER_LINEAR) coordinate rule.  cv2 has two: the one-channel f32 resize of the level images goes
+// through its IPP path, which keeps the coordinate in double; the two-channel resize of the flow field (A.2) runs OpenCV's
+// generic path, which rounds the coordinate to f32 BEFORE the floor (`fx = (float)((dx+0.5)*scale_x - 0.5)`).  Both measured
+// against the installed wheel (tests/test_oracle_vs_golden.py::test_resize_coordinate_rules_of_cv2); they only differ when
+// the scale is not dyadic (pyr_scale != 0.5 or odd sizes).
+void linear_table(int dst, int src, std::vector<int>& idx, std::vector<float>& w1, bool f32_coord = false)
 {
     idx.resize(dst); w1.resize(dst);
     double scale = 1.0 / ((double)dst / src);
     for (int d = 0; d < dst; d++) {
         double f = (d + 0.5) * scale - 0.5;
+        if (f32_coord) f = (double)(float)f;
         int s = (int)std::floor(f);
         f -= s;
         if (s < 0) { s = 0; f = 0; }
@@ -362,8 +367,8 @@ int ensure_plan(ofb_context* ctx, int W, int H, int dtype, const ofb_params* p, 
         if (k < pl.K) {
             int Wc, Hc, ksc; double sgc;
             scale_geometry(W, H, p->pyr_scale, k + 1, &Wc, &Hc, &ksc, &sgc, nullptr);
-            linear_table(l.W, Wc, ix, wx);
-            linear_table(l.H, Hc, iy, wy);
+            linear_table(l.W, Wc, ix, wx, true);             // flow up-sample: generic path, f32 coordinate
+            linear_table(l.H, Hc, iy, wy, true);
             if (int rc = dupload(ctx, pl, &l.ux, ix)) return rc;
             if (int rc = dupload(ctx, pl, &l.uax, wx)) return rc;
             if (int rc = dupload(ctx, pl, &l.uy, iy)) return rc;

@@ -20,8 +20,8 @@ k_upsample_flow(const float2* __restrict__ prev, int Wp, int Hp, float2* __restr
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
     float a1, b1;
-    int sx = linear_coord(x, sx_scale, Wp, &a1);
-    int sy = linear_coord(y, sy_scale, Hp, &b1);
+    int sx = linear_coord(x, sx_scale, Wp, &a1, true);
+    int sy = linear_coord(y, sy_scale, Hp, &b1, true);
     float a0 = 1.f - a1, b0 = 1.f - b1;
     int sx1 = min(sx + 1, Wp - 1), sy1 = min(sy + 1, Hp - 1);
     float2 p00 = prev[(size_t)sy * Wp + sx], p01 = prev[(size_t)sy * Wp + sx1];

@@ -177,7 +177,7 @@ def gauss_taps_half(winsize):
     return k
 
 
-def upsample_flow(prev, W, H, pyr_scale, float_coords=0):
+def upsample_flow(prev, W, H, pyr_scale, float_coords=1):
     prev = _f32(prev)
     Hp, Wp = prev.shape[:2]
     out = np.empty((H, W, 2), np.float32)

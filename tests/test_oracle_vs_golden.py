@@ -159,3 +159,25 @@ def test_jpeg_oracle_against_the_installed_cv2_on_fresh_pictures(oracle):
         ref = cv2.imencode(".jpeg", img, [cv2.IMWRITE_JPEG_QUALITY, q])[1].ravel()
         got = oracle.jpeg_encode(img, q)
         assert np.array_equal(got, ref), (h, w, q)
+
+
+def test_resize_coordinate_rules_of_cv2(oracle):
+    """cv::resize(INTER_LINEAR) has two coordinate rules in the wheel (round-1 advisor finding): the one-channel f32 resize of
+    the level images keeps the source coordinate in double, the two-channel resize of the flow field rounds it
+    to f32 before the floor.  The oracle (and the engine's tables) use each where cv2 does.  Runs against the installed cv2;
+    the wrong rule is two orders of magnitude further away on a non-dyadic scale."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for ws, hs, wd, hd in [(140, 105, 200, 150), (864, 486, 1080, 608), (98, 74, 140, 105)]:
+        flow = rng.normal(0, 100, (hs, ws, 2)).astype(np.float32)
+        ref = cv2.resize(flow, (wd, hd), interpolation=cv2.INTER_LINEAR)
+        right = np.abs(oracle.resize_linear(flow, wd, hd, float_coords=1) - ref).max()
+        wrong = np.abs(oracle.resize_linear(flow, wd, hd, float_coords=0) - ref).max()
+        assert right <= 1e-4 and wrong > 10 * right, ("flow", ws, wd, right, wrong)        # 1e-4 on values of ~100: 1-2 ulp
+        assert np.array_equal(oracle.upsample_flow(flow, wd, hd, 0.7),
+                              oracle.resize_linear(flow, wd, hd, float_coords=1) * np.float32(1 / 0.7))
+        img = rng.normal(0, 100, (hs, ws)).astype(np.float32)
+        ref = cv2.resize(img, (wd, hd), interpolation=cv2.INTER_LINEAR)
+        right = np.abs(oracle.resize_linear(img, wd, hd, float_coords=0) - ref).max()
+        wrong = np.abs(oracle.resize_linear(img, wd, hd, float_coords=1) - ref).max()
+        assert right <= 1e-4 and wrong > 10 * right, ("image", ws, wd, right, wrong)
