@@ -26,6 +26,9 @@
 #include "launch.cuh"
 #include "um_device.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
 
 namespace ofb {
 
@@ -42,41 +45,83 @@ namespace ofb {
 #endif
 constexpr int UM0_BX = OFB_UM0_BX, UM0_BY = OFB_UM0_BY;
 
+#ifndef OFB_UM0_ROWS
+#define OFB_UM0_ROWS 4
+#endif
+#ifndef OFB_UM0_MINB
+#define OFB_UM0_MINB 8
+#endif
+constexpr int UM0_ROWS = OFB_UM0_ROWS;    // consecutive rows per thread (a sequential loop, not ILP): the slot / base-pointer
+                                          // arithmetic and the per-column table loads -- a quarter of the instructions of the
+                                          // one-pixel-per-thread version, which ran at 72 % issue utilisation -- are paid once
+
 template <int SRC>   // 0 zero flow, 1 read flow, 2 up-sample coarse flow
-__global__ void __launch_bounds__(UM0_BX * UM0_BY)
+__global__ void __launch_bounds__(UM0_BX * UM0_BY, OFB_UM0_MINB)
 k_um0(Um0Args a)
 {
     // blockIdx.x = batch item (fastest-varying in dispatch order): the CTAs of consecutive pairs for the same tile
     // run together, so the frame slot pair z reads as R1 and pair z+1 reads as R0 comes from HBM once.
-    const int x = blockIdx.y * UM0_BX + threadIdx.x, y = blockIdx.z * UM0_BY + threadIdx.y, z = blockIdx.x;
-    if (x >= a.W || y >= a.H) return;
-    float dx = 0.f, dy = 0.f;
-    if (SRC == 1) {
-        float2 d = a.flow[(size_t)z * a.flow_item + (size_t)y * a.W + x];
-        dx = d.x; dy = d.y;
-    } else if (SRC == 2) {
-        const float2* prev = a.flow + (size_t)z * a.flow_item;
-        const int sx = a.ux[x], sy = a.uy[y];
-        const float a1 = a.uax[x], b1 = a.uay[y];
-        float a0 = 1.f - a1, b0 = 1.f - b1;
-        int sx1 = min(sx + 1, a.Wp - 1), sy1 = min(sy + 1, a.Hp - 1);
-        float2 p00 = prev[(size_t)sy * a.Wp + sx], p01 = prev[(size_t)sy * a.Wp + sx1];
-        float2 p10 = prev[(size_t)sy1 * a.Wp + sx], p11 = prev[(size_t)sy1 * a.Wp + sx1];
-        float hx0 = p00.x * a0 + p01.x * a1, hx1 = p10.x * a0 + p11.x * a1;
-        float hy0 = p00.y * a0 + p01.y * a1, hy1 = p10.y * a0 + p11.y * a1;
-        dx = (hx0 * b0 + hx1 * b1) * a.mul;
-        dy = (hy0 * b0 + hy1 * b1) * a.mul;
+    const int x = blockIdx.y * UM0_BX + threadIdx.x, z = blockIdx.x;
+    const int ybeg = (blockIdx.z * UM0_BY + threadIdx.y) * UM0_ROWS;
+    // The two per-item bases go through a warp shuffle: ptxas otherwise folds z * item into EVERY address of the loop (a 64-bit
+    // multiply-add, LEA and LEA.HI.X per load / store: 50 instructions per pixel); a shuffled pointer is just a register pair.
+    float* const mout = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(a.M + (size_t)z * a.m_item), 0));
+    const float2* const fl = reinterpret_cast<const float2*>(      // SRC 1: this scale's flow; SRC 2: the coarser one
+        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(a.flow + (size_t)z * a.flow_item), 0));
+    __builtin_assume(__isGlobal(mout));
+    __builtin_assume(__isGlobal(fl));
+    if (x >= a.W || ybeg >= a.H) return;
+    const int yend = min(ybeg + UM0_ROWS, a.H);
+    const UmBase ub = um_base(a.R, a.slot0, z);                 // M and R of a level share pitch and plane size (launch_um0)
+    const int W = a.W, H = a.H;
+    const unsigned plane = (unsigned)a.plane;
+    unsigned o0 = (unsigned)ybeg * (unsigned)a.pitch + (unsigned)x;
+    unsigned sx = 0, sx1 = 0;
+    float a1 = 0.f, a0 = 1.f;
+    if (SRC == 2) {
+        sx = a.ux[x]; a1 = a.uax[x];
+        a0 = 1.f - a1;
+        sx1 = min(sx + 1, (unsigned)a.Wp - 1);
     }
-    const int s0 = a.R.first(a.slot0, z), s1 = a.R.wrap(s0 + 1);
-    M5 m = um_pixel(x, y, dx, dy, a.R.slot(s0), a.R.slot(s1), a.W, a.H);
-    float* out = a.M + (size_t)z * a.m_item + (size_t)y * a.pitch + x;
+#pragma unroll 1
+    for (int y = ybeg; y < yend; y++, o0 += a.pitch) {
+        float dx = 0.f, dy = 0.f;
+        if (SRC == 1) {
+            float2 d = fl[(unsigned)y * (unsigned)W + (unsigned)x];
+            dx = d.x; dy = d.y;
+        } else if (SRC == 2) {
+            const int sy = a.uy[y];
+            const float b1 = a.uay[y], b0 = 1.f - b1;
+            const unsigned o0 = (unsigned)sy * (unsigned)a.Wp;                  // one item of the coarse flow is far below 2^32 pixels
+            const unsigned o1 = (unsigned)min(sy + 1, a.Hp - 1) * (unsigned)a.Wp;
+            // hx = p0.x*a0 + p1.x*a1 per row, d = (h0*b0 + h1*b1) * mul: products packed over (x, y), adds scalar (um_device.cuh)
+            const float2 t00 = mul2s(fl[o0 + sx], a0), t01 = mul2s(fl[o0 + sx1], a1);
+            const float2 t10 = mul2s(fl[o1 + sx], a0), t11 = mul2s(fl[o1 + sx1], a1);
+            const float2 h0 = mul2s(make_float2(t00.x + t01.x, t00.y + t01.y), b0);
+            const float2 h1 = mul2s(make_float2(t10.x + t11.x, t10.y + t11.y), b1);
+            const float2 d = mul2s(make_float2(h0.x + h1.x, h0.y + h1.y), a.mul);
+            dx = d.x; dy = d.y;
+        }
+        M5 m = um_pixel(x, y, o0, dx, dy, ub, W, H);
 #pragma unroll
-    for (int c = 0; c < 5; c++) out[(size_t)c * a.plane] = m.v[c];
+        for (int c = 0; c < 5; c++) mout[o0 + c * plane] = m.v[c];          // 5 * plane < 2^32 floats
+    }
+}
+
+// The kernels address M and R of a level with ONE pixel offset y * pitch + x (32 bits): both must share pitch and plane size, and
+// a batch item must stay below 2^32 floats.  Every call site in engine.cu allocates them that way; anything else is a bug here.
+static void check_shared_layout(const SlotRing& R, size_t plane, int pitch)
+{
+    if (R.pitch != pitch || R.plane != plane || 5 * plane >= (1ull << 32)) {
+        fprintf(stderr, "ofb: internal error: M / R layout mismatch (pitch %d vs %d, plane %zu vs %zu)\n", pitch, R.pitch, plane, R.plane);
+        abort();
+    }
 }
 
 void launch_um0(Launch& L, int src, const Um0Args& a, int batch)
 {
-    dim3 block(UM0_BX, UM0_BY), grid(batch, divup(a.W, UM0_BX), divup(a.H, UM0_BY));
+    check_shared_layout(a.R, a.plane, a.pitch);
+    dim3 block(UM0_BX, UM0_BY), grid(batch, divup(a.W, UM0_BX), divup(a.H, UM0_BY * UM0_ROWS));
     const char* names[3] = {"um0_zero", "um0_flow", "um0_upsample"};
     L.run(names[src], [&](cudaStream_t s) {
         if (src == 0) k_um0<0><<<grid, block, 0, s>>>(a);
@@ -124,7 +169,8 @@ k_iter(IterArgs a)
     const int bx = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
     const int bs = a.reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
     const int W = a.W, H = a.H;
-    const int x0 = bx * TW;
+    // first column of the tile; through a shuffle so that it stays in a register (see k_iter64)
+    const int x0 = (FUSE && ILP == 1) ? __shfl_sync(0xffffffffu, bx * TW, 0) : bx * TW;
     const int ybeg = bs * a.strip_rows;
     const int yend = min(ybeg + a.strip_rows, H);
     if (ybeg >= H) return;
@@ -138,16 +184,22 @@ k_iter(IterArgs a)
 #pragma unroll
     for (int i = 0; i < R; i++) blkA[i] = src[(size_t)min(max(ybeg - M + i, 0), H - 1) * pitch];
 
-    RView R0{nullptr, nullptr, 0}, R1{nullptr, nullptr, 0};
+    // Output base of this batch item, pinned in a register pair through a warp shuffle (see k_um0), and the two R slots.
+    // M and R of a level share pitch and plane size, so one pixel offset o0 = y * pitch + x (32 bits) addresses all of them.
+    UmBase ub{nullptr, nullptr, 0u, 0};
+    RView R0{nullptr, nullptr, 0}, R1{nullptr, nullptr, 0};            // for the prefetch addresses and the ILP > 1 path
     float* mout = nullptr;
     float2* fout = nullptr;
     if (FUSE) {
-        const int s0 = a.R.first(a.slot0, z), s1 = a.R.wrap(s0 + 1);
-        R0 = a.R.slot(s0); R1 = a.R.slot(s1);
-        mout = a.Mout + (size_t)z * a.m_item;
+        ub = um_base(a.R, a.slot0, z);
+        R0 = RView{const_cast<float4*>(ub.r0), const_cast<float*>(reinterpret_cast<const float*>(ub.r0)) + ub.plane4, pitch};
+        R1 = RView{const_cast<float4*>(ub.r1), const_cast<float*>(reinterpret_cast<const float*>(ub.r1)) + ub.plane4, pitch};
+        mout = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(a.Mout + (size_t)z * a.m_item), 0));
+        __builtin_assume(__isGlobal(mout));
     } else {
         fout = a.flow + (size_t)z * a.flow_item;
     }
+    const unsigned mplane = (unsigned)a.plane;
 
     float mag_lo = __int_as_float(0x7f800000), mag_hi = 0.f;      // per-thread min / max of |flow| (a.minmax)
 
@@ -270,32 +322,43 @@ k_iter(IterArgs a)
 
         // ---- S phase: item = pixel ----
         if (ILP == 1) {
-            for (int i = tid; i < R * TW; i += IT_THREADS) {
-                const int r = i / TW, lx = i - r * TW;
-                const int y = ys + r, x = x0 + lx;
-                if (y < yend && x < W) {
-                    const float* h = sH + r * HP + lx;
-                    const float g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
-                    // flow = [g11*h2 - g12*h1, g22*h1 - g12*h2] * scale^2 / ((g11*g22 - g12^2) * scale^2 + 1e-3)
-                    //      = [ ... ] / (g11*g22 - g12^2 + 1e-3 / scale^2)
-                    const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
-                    const float idet = __frcp_rn(det);
-                    const float fx = __fmul_rn(kahan_det(g11, h2, g12, h1), idet);
-                    const float fy = __fmul_rn(kahan_det(g22, h1, g12, h2), idet);
-                    if (FUSE) {
-                        M5 m = um_pixel(x, y, fx, fy, R0, R1, W, H);
-                        float* o = mout + (size_t)y * pitch + x;
+            // A thread's items are tid, tid + T, ...: (r, lx) advance by (T / TW, T % TW) with a carry instead of a division per
+            // pixel.  `interior` (block-uniform): no pixel of this step is within 5 px of a border, so UpdateMatrices skips the
+            // per-pixel border test.
+            auto s_phase = [&](auto interior_tag) {
+                constexpr bool INTERIOR = decltype(interior_tag)::value;
+                constexpr int DR = IT_THREADS / TW, DL = IT_THREADS % TW;
+                int r = tid / TW, lx = tid - r * TW;
+                while (r < R) {
+                    const int y = ys + r, x = x0 + lx;
+                    if (y < yend && x < W) {
+                        const float* h = sH + r * HP + lx;
+                        const float g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
+                        // flow = [g11*h2 - g12*h1, g22*h1 - g12*h2] * scale^2 / ((g11*g22 - g12^2) * scale^2 + 1e-3)
+                        //      = [ ... ] / (g11*g22 - g12^2 + 1e-3 / scale^2)
+                        const float det = __fadd_rn(kahan_det(g11, g22, g12, g12), a.c);
+                        const float idet = __frcp_rn(det);
+                        const float fx = __fmul_rn(kahan_det(g11, h2, g12, h1), idet);
+                        const float fy = __fmul_rn(kahan_det(g22, h1, g12, h2), idet);
+                        if (FUSE) {
+                            const unsigned o0 = (unsigned)y * (unsigned)pitch + (unsigned)x;
+                            M5 m = um_pixel<INTERIOR>(x, y, o0, fx, fy, ub, W, H);
 #pragma unroll
-                        for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
-                    } else {
-                        fout[(size_t)y * W + x] = make_float2(fx, fy);
-                        if (a.minmax) {                        // cv::cartToPolar's magnitude, as in viz.cu
-                            const float mg = sqrtf(fmaf(fx, fx, fy * fy));
-                            mag_lo = fminf(mag_lo, mg); mag_hi = fmaxf(mag_hi, mg);
+                            for (int c = 0; c < 5; c++) mout[o0 + c * mplane] = m.v[c];
+                        } else {
+                            fout[(unsigned)y * (unsigned)W + (unsigned)x] = make_float2(fx, fy);
+                            if (a.minmax) {                        // cv::cartToPolar's magnitude, as in viz.cu
+                                const float mg = sqrtf(fmaf(fx, fx, fy * fy));
+                                mag_lo = fminf(mag_lo, mg); mag_hi = fmaxf(mag_hi, mg);
+                            }
                         }
                     }
+                    r += DR; lx += DL;
+                    if (lx >= TW) { lx -= TW; ++r; }
                 }
-            }
+            };
+            if (FUSE && x0 >= 5 && x0 + TW <= W - 5 && ys >= 5 && ys + R <= H - 5) s_phase(std::true_type{});
+            else s_phase(std::false_type{});
         } else {
             for (int i0 = tid; i0 < R * TW; i0 += ILP * IT_THREADS) {
                 UmLoads L[ILP];
@@ -322,9 +385,9 @@ k_iter(IterArgs a)
                     for (int j = 0; j < ILP; j++) {
                         if (ok[j]) {
                             M5 m = um_compute(L[j], W, H);
-                            float* o = mout + (size_t)L[j].y * pitch + L[j].x;
+                            const unsigned o0 = (unsigned)L[j].y * (unsigned)pitch + (unsigned)L[j].x;
 #pragma unroll
-                            for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
+                            for (int c = 0; c < 5; c++) mout[o0 + c * mplane] = m.v[c];
                         }
                     }
                 }
@@ -437,7 +500,9 @@ k_iter64(IterArgs a)
     const int tid = threadIdx.x;
     const int z = blockIdx.x, bx = blockIdx.y, bs = blockIdx.z;
     const int W = a.W, H = a.H;
-    const int x0 = bx * TW;
+    // first column of the tile; through a shuffle so that it stays in a register (ptxas otherwise re-reads %ctaid.y and
+    // multiplies again at every use inside the S phase)
+    const int x0 = FUSE ? __shfl_sync(0xffffffffu, bx * TW, 0) : bx * TW;
     const int ybeg = bs * a.strip_rows;
     const int yend = min(ybeg + a.strip_rows, H);
     if (ybeg >= H) return;
@@ -448,30 +513,46 @@ k_iter64(IterArgs a)
     const int pitch = a.pitch;
 
     // old[r] = the row that LEAVES the window when it moves down to row ys + r:  max(ys + r - M - 1, 0)
+#ifdef OFB_I64_RELOAD_OLD
+    // The leaving rows are loaded again (they entered one step ago: L2 hits) instead of being carried in R registers across the
+    // H and S phases, whose UpdateMatrices working set otherwise makes ptxas re-derive tile coordinates and shuffle pairs.
+    float old0 = src[(size_t)min(max(ybeg - M - 1, 0), H - 1) * pitch];
+#else
     float old[R];
 #pragma unroll
     for (int i = 0; i < R; i++) old[i] = ld_stream(src + (size_t)min(max(ybeg - M - 1 + i, 0), H - 1) * pitch);
+#endif
     // S = cv2's vsum BEFORE row ybeg is processed.  At the top of the image that is float(row0 * (m+2)) + rows 1..m-1;
     // a strip that starts lower (not used by the exact mode) starts from the plain sum of the window of row ybeg - 1.
     double S;
     if (ybeg == 0) {
+#ifdef OFB_I64_RELOAD_OLD
+        S = (double)__fmul_rn(old0, (float)(M + 2));
+#else
         S = (double)__fmul_rn(old[0], (float)(M + 2));
+#endif
         for (int y = 1; y < M; y++) S += (double)src[(size_t)min(y, H - 1) * pitch];
     } else {
         S = 0.0;
         for (int j = ybeg - 1 - M; j <= ybeg - 1 + M; j++) S += (double)src[(size_t)min(max(j, 0), H - 1) * pitch];
     }
 
-    RView R0{nullptr, nullptr, 0}, R1{nullptr, nullptr, 0};
+    // Output base of this batch item, pinned in a register pair through a warp shuffle (see k_um0), and the two R slots.
+    // M and R of a level share pitch and plane size, so one pixel offset o0 = y * pitch + x (32 bits) addresses all of them.
+    UmBase ub{nullptr, nullptr, 0u, 0};
+    RView R0{nullptr, nullptr, 0}, R1{nullptr, nullptr, 0};            // only for the prefetch addresses
     float* mout = nullptr;
     float2* fout = nullptr;
     if (FUSE) {
-        const int s0 = a.R.first(a.slot0, z), s1 = a.R.wrap(s0 + 1);
-        R0 = a.R.slot(s0); R1 = a.R.slot(s1);
-        mout = a.Mout + (size_t)z * a.m_item;
+        ub = um_base(a.R, a.slot0, z);
+        R0 = RView{const_cast<float4*>(ub.r0), const_cast<float*>(reinterpret_cast<const float*>(ub.r0)) + ub.plane4, pitch};
+        R1 = RView{const_cast<float4*>(ub.r1), const_cast<float*>(reinterpret_cast<const float*>(ub.r1)) + ub.plane4, pitch};
+        mout = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(a.Mout + (size_t)z * a.m_item), 0));
+        __builtin_assume(__isGlobal(mout));
     } else {
         fout = a.flow + (size_t)z * a.flow_item;
     }
+    const unsigned mplane = (unsigned)a.plane;
     const double c64 = a.c64;
     float mag_lo = __int_as_float(0x7f800000), mag_hi = 0.f;
 
@@ -518,11 +599,26 @@ k_iter64(IterArgs a)
         }
         {
             double* v = sV + vc * R * I64_VP + vcol;
+#ifdef OFB_I64_RELOAD_OLD
+            float old[R];
+            if (ys - M - 1 >= 0) {
+                const float* po = src + (size_t)(ys - M - 1) * pitch;      // rows ys-M-1 .. ys+M-1 < H: no clamp
+#pragma unroll
+                for (int r = 0; r < R; r++) old[r] = (ys - M - 1 + r < H) ? po[r * pitch] : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; r++) if (ys - M - 1 + r >= H) old[r] = src[(size_t)(H - 1) * pitch];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) old[r] = src[(size_t)min(max(ys - M - 1 + r, 0), H - 1) * pitch];
+            }
+#endif
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 S += (double)__fsub_rn(nb[r], old[r]);                 // cv2: vsum[x] += srow1[x] - srow0[x]  (float difference)
                 v[r * I64_VP] = S;                                      // window of row ys + r
+#ifndef OFB_I64_RELOAD_OLD
                 old[r] = nb[r];                                        // the rows that entered now leave during the next step
+#endif
             }
         }
         __syncthreads();
@@ -551,35 +647,45 @@ k_iter64(IterArgs a)
         }
         __syncthreads();
 
-        // ---- S phase: item = pixel ----
-        for (int i = tid; i < R * TW; i += I64_THREADS) {
-            const int r = i / TW, lx = i - r * TW;
-            const int y = ys + r, x = x0 + lx;
-            if (y < yend && x < W) {
-                const double* h = sH + r * HP + lx;
-                const double g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
-                // cv2: idet = 1 / (g11*g22 - g12^2 + 1e-3) on sums scaled by 1/w^2; here unscaled sums, c64 = 1e-3 * w^4.  The
-                // three cancelling differences stay in f64 (DFMA); only the well-conditioned quotient is formed in f32.
-                const double det = fma(g11, g22, -(g12 * g12)) + c64;
-                const double nx = fma(g11, h2, -(g12 * h1));
-                const double ny = fma(g22, h1, -(g12 * h2));
-                const float idet = __frcp_rn((float)det);
-                const float fx = __fmul_rn((float)nx, idet);
-                const float fy = __fmul_rn((float)ny, idet);
-                if (FUSE) {
-                    M5 m = um_pixel(x, y, fx, fy, R0, R1, W, H);
-                    float* o = mout + (size_t)y * pitch + x;
+        // ---- S phase: item = pixel.  A thread's items are tid, tid + T, ...: (r, lx) advance by (T / TW, T % TW) with a carry
+        // instead of a division per pixel.  `interior` (block-uniform): no pixel of this step is within 5 px of a border, so
+        // UpdateMatrices skips the per-pixel border test (22 of 24 tiles, 70 of 72 steps at 1080p). ----
+        auto s_phase = [&](auto interior_tag) {
+            constexpr bool INTERIOR = decltype(interior_tag)::value;
+            constexpr int DR = I64_THREADS / TW, DL = I64_THREADS % TW;
+            int r = tid / TW, lx = tid - r * TW;
+            while (r < R) {
+                const int y = ys + r, x = x0 + lx;
+                if (y < yend && x < W) {
+                    const double* h = sH + r * HP + lx;
+                    const double g11 = h[0], g12 = h[R * HP], g22 = h[2 * R * HP], h1 = h[3 * R * HP], h2 = h[4 * R * HP];
+                    // cv2: idet = 1 / (g11*g22 - g12^2 + 1e-3) on sums scaled by 1/w^2; here unscaled sums, c64 = 1e-3 * w^4.  The
+                    // three cancelling differences stay in f64 (DFMA); only the well-conditioned quotient is formed in f32.
+                    const double det = fma(g11, g22, -(g12 * g12)) + c64;
+                    const double nx = fma(g11, h2, -(g12 * h1));
+                    const double ny = fma(g22, h1, -(g12 * h2));
+                    const float idet = __frcp_rn((float)det);
+                    const float fx = __fmul_rn((float)nx, idet);
+                    const float fy = __fmul_rn((float)ny, idet);
+                    if (FUSE) {
+                        const unsigned o0 = (unsigned)y * (unsigned)pitch + (unsigned)x;
+                        M5 m = um_pixel<INTERIOR>(x, y, o0, fx, fy, ub, W, H);
 #pragma unroll
-                    for (int c = 0; c < 5; c++) o[(size_t)c * a.plane] = m.v[c];
-                } else {
-                    fout[(size_t)y * W + x] = make_float2(fx, fy);
-                    if (a.minmax) {
-                        const float mg = sqrtf(fmaf(fx, fx, fy * fy));
-                        mag_lo = fminf(mag_lo, mg); mag_hi = fmaxf(mag_hi, mg);
+                        for (int c = 0; c < 5; c++) mout[o0 + c * mplane] = m.v[c];
+                    } else {
+                        fout[(unsigned)y * (unsigned)W + (unsigned)x] = make_float2(fx, fy);
+                        if (a.minmax) {
+                            const float mg = sqrtf(fmaf(fx, fx, fy * fy));
+                            mag_lo = fminf(mag_lo, mg); mag_hi = fmaxf(mag_hi, mg);
+                        }
                     }
                 }
+                r += DR; lx += DL;
+                if (lx >= TW) { lx -= TW; ++r; }
             }
-        }
+        };
+        if (FUSE && x0 >= 5 && x0 + TW <= W - 5 && ys >= 5 && ys + R <= H - 5) s_phase(std::true_type{});
+        else s_phase(std::false_type{});
         // no barrier here: the next V phase writes only sV (last read before the barrier above); sH is next written after
         // the barrier that follows that V phase.
     }
@@ -615,6 +721,7 @@ bool iter_supported(int winsize) { int m = winsize / 2; return m >= 1 && m <= 16
 
 void launch_iter(Launch& L, const IterArgs& a, int winsize, bool fuse_um, int batch)
 {
+    if (fuse_um) check_shared_layout(a.R, a.plane, a.pitch);
     const int m = winsize / 2;
     if (a.gauss) {
         switch (m) {
