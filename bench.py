@@ -255,9 +255,10 @@ def parity_check(eng, frames, W, H, P):
     except Exception as e:     # cv2 missing on this box: say so, do not invent a number
         return {"checked": False, "why": "cv2 not importable: %r" % (e,)}
     n = W * H
-    B = 24 if (W, H) == (1920, 1080) else 0
-    pairs = sorted({t for t in (0, B // 4 - 1, B // 4, 3 * B // 4 - 1, 3 * B // 4, 2 * B - 1, 2 * B, P // 2,
-                                P - B // 4 - 1, P - B // 4, P - 1) if 0 <= t < P})
+    B = eng.shot_chunk(W, H, P)
+    starts = eng.chunk_starts(W, H, P)
+    seams = starts[1:3] + starts[-1:]                       # after the B/4 and the B/2 head chunk, before the last tail chunk
+    pairs = sorted({t for t in [0, 2 * B - 1, 2 * B, P // 2, P - 1] + [s - 1 for s in seams] + seams if 0 <= t < P})
     d_frames = eng.device_alloc(frames.nbytes)
     d_bgr = eng.device_alloc(P * n * 3)
     d_flow = eng.device_alloc(P * n * 8)

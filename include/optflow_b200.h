@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define OFB_ABI_VERSION 3
+#define OFB_ABI_VERSION 4
 
 /* flags of cv2.calcOpticalFlowFarneback */
 #define OFB_OPTFLOW_USE_INITIAL_FLOW 4
@@ -149,6 +149,11 @@ int ofb_pairs_host(ofb_context* ctx, const uint8_t* prev, const uint8_t* next, i
                    const ofb_params* p, uint8_t* bgr, float* magsum, float* flow, float* device_ms);
 int ofb_shot_device(ofb_context* ctx, const uint8_t* d_frames, int n_frames, int W, int H, const ofb_params* p,
                     uint8_t* d_bgr, float* d_magsum, float* d_flow, float* device_ms);
+/* Pairs per launch ("chunk") the ofb_shot_* / ofb_pairs_* entry points use for W x H frames and a job of n_pairs pairs: option
+ * "batch" when it is set, else enough pixels per launch to fill the GPU at the coarse scales (96e6 / (W*H), a multiple of 4; a
+ * job shorter than four such chunks is cut into about four).  A long job runs chunks of B/4, B/2, B, ..., B, B/2, B/4 pairs; results never depend on the chunking (tests pin that), the
+ * function exists so that tests and bench.py can aim their parity checks at the chunk seams. */
+int ofb_shot_chunk(const ofb_context* ctx, int W, int H, int n_pairs);
 
 /* ---- frame preprocessing on the GPU -------------------
  * Both are integer algorithms and bit-exact against cv2 (tests/golden/preprocess.npz).

@@ -100,6 +100,7 @@ def load():
     proto("ofb_stage_upsample_flow", i, vp, vp, i, i, i, i, C.c_double, vp)
     proto("ofb_debug_check_guards", i, vp)
     proto("ofb_set_option", i, vp, C.c_char_p, i)
+    proto("ofb_shot_chunk", i, vp, i, i, i)
     proto("ofb_get_kernel_stats", i, vp, C.POINTER(KernelStat), i)
     proto("ofb_reset_kernel_stats", None, vp)
     proto("ofb_algorithmic_bytes_pair", C.c_double, i, i, pp)

@@ -608,9 +608,20 @@ int shot_batch(const ofb_context* ctx, int W, int H, int n_pairs)
 {
     int b = ctx->batch;
     if (b <= 0) {
+        // 1080p: 48.  Measured on B200 (300-pair shot, default arithmetic, profiles/r2x_ab_batch.log): 24 / 37 / 48 / 74 pairs per
+        // launch give 4078 / 4069 / 4171 / 4061 pairs/s.  k_iter64 walks a whole column per CTA, so a launch has batch x 24 long
+        // CTAs for 296 resident ones: 48 is 3.9 waves at scale 0 and fills the GPU at the two coarser scales (24 left half of
+        // it idle at 480x270); beyond that the per-launch working set leaves L2.
         double px = (double)W * H;
-        b = (int)std::ceil(48.0e6 / px);
+        b = (int)std::ceil(96.0e6 / px);
+        b = (b + 3) / 4 * 4;
         b = std::max(4, std::min(b, 512));
+        // A job shorter than four such chunks (a short shot, one rank's share of a sharded shot) is cut into about four, but not
+        // below b / 4: upload, kernels and download of consecutive chunks overlap, one big chunk would serialise them.
+        if (n_pairs < 4 * b) {
+            const int q = ((n_pairs + 3) / 4 + 3) / 4 * 4;
+            b = std::max(std::max(4, b / 4), std::min(q, b));
+        }
     }
     return std::max(1, std::min(b, std::min(n_pairs, MAX_BATCH)));
 }
@@ -1616,6 +1627,12 @@ int ofb_debug_check_guards(ofb_context* ctx)
     if (int rc = scan(ctx->plan.guards)) return rc;
     if (int rc = scan(ctx->jpeg_guards)) return rc;
     return bad;
+}
+
+int ofb_shot_chunk(const ofb_context* ctx, int W, int H, int n_pairs)
+{
+    if (!ctx || W <= 0 || H <= 0 || n_pairs <= 0) return 0;
+    return shot_batch(ctx, W, H, n_pairs);
 }
 
 int ofb_set_option(ofb_context* ctx, const char* name, int value)

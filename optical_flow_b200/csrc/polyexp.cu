@@ -595,6 +595,10 @@ struct PeFast {
     static constexpr int PO = SRC == 0 ? -1 : 0;                                // first patch column of pair 0 (keeps float2 loads aligned)
     static constexpr int NPAIR = SRC == 0 ? PW / 2 + 1 : PW / 2;
     static constexpr int SMEM = 3 * TH * RP * 8 + (SRC == 0 ? 0 : RAWH * HBP * 4);
+    // Exact arithmetic keeps the f32 vertical results AS f32 in the same arrays (row pitch FP floats: a multiple of 4 for the
+    // float4 window loads, FP / 4 odd so that the 8 rows of a quarter-warp fall in distinct bank groups).
+    static constexpr int FP0 = (PW + 3) / 4 * 4, FP = (FP0 / 4) % 2 == 1 ? FP0 : FP0 + 4;
+    static_assert(FP <= 2 * RP, "the f32 rows fit in the f64 rows' space");
     static_assert(PE_TH == 16 && (RP / 2) % 2 == 1 && VGROUPS * NPAIR <= PE_THREADS, "tile geometry of the fast path");
 };
 
@@ -707,6 +711,21 @@ __device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* p
                     r2 = pe_fma2(sp, a.xxg[k], r2);
                 }
             }
+            if (exact) {
+                // cv2's row buffers are f32: stored as they are (round 2, last session: the widening here and the narrowing in
+                // the horizontal pass were 14 of the 47 conversions per pixel that keep the XU pipe busy)
+                float* f0 = reinterpret_cast<float*>(sR0), *f1 = reinterpret_cast<float*>(sR1), *f2 = reinterpret_cast<float*>(sR2);
+                const int ef = (r0row + o) * G::FP + px;
+                if (G::PO == 0) {
+                    *reinterpret_cast<float2*>(f0 + ef) = r0;
+                    *reinterpret_cast<float2*>(f1 + ef) = r1;
+                    *reinterpret_cast<float2*>(f2 + ef) = r2;
+                } else {
+                    if (px >= 0) { f0[ef] = r0.x; f1[ef] = r1.x; f2[ef] = r2.x; }
+                    if (px + 1 < G::PW) { f0[ef + 1] = r0.y; f1[ef + 1] = r1.y; f2[ef + 1] = r2.y; }
+                }
+                continue;
+            }
             const int e = (r0row + o) * RP + px;
             if (G::PO == 0) {
                 *reinterpret_cast<double2*>(sR0 + e) = make_double2((double)r0.x, (double)r0.y);
@@ -727,11 +746,19 @@ __device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* p
     float o0[4], o1[4], o2[4], o3[4], o4[4];
     double c1[4];
     if (exact) {
-        // cv2's float / double mix, as in pe_tile (the shared arrays hold the f32 vertical results widened exactly)
+        // cv2's float / double mix, as in pe_tile; the shared arrays hold the f32 vertical results as f32 (pitch G::FP)
         float w[4 + 2 * N];
-        const double2* q = reinterpret_cast<const double2*>(sR0 + ly * RP + lx0);
+        auto load_window = [&](const double* arr) {
+            const float* q = reinterpret_cast<const float*>(arr) + ly * G::FP + lx0;       // 16-byte aligned
 #pragma unroll
-        for (int j = 0; j < (4 + 2 * N) / 2; j++) { const double2 t = q[j]; w[2 * j] = (float)t.x; w[2 * j + 1] = (float)t.y; }
+            for (int j = 0; j < (4 + 2 * N) / 4; j++) {
+                const float4 t = reinterpret_cast<const float4*>(q)[j];
+                w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+            }
+            const float2 t = *reinterpret_cast<const float2*>(q + (4 + 2 * N) / 4 * 4);    // 4 + 2N = 4m + 2 (N odd)
+            w[(4 + 2 * N) / 4 * 4] = t.x; w[(4 + 2 * N) / 4 * 4 + 1] = t.y;
+        };
+        load_window(sR0);
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             double b1 = (double)__fmul_rn(w[o + N], a.g[0]), b2 = 0, b4 = 0;
@@ -746,9 +773,7 @@ __device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* p
             o1[o] = (float)__dmul_rn(b2, a.ig11);
             o3[o] = (float)__dadd_rn(c1[o], __dmul_rn(b4, a.ig33));
         }
-        q = reinterpret_cast<const double2*>(sR2 + ly * RP + lx0);
-#pragma unroll
-        for (int j = 0; j < (4 + 2 * N) / 2; j++) { const double2 t = q[j]; w[2 * j] = (float)t.x; w[2 * j + 1] = (float)t.y; }
+        load_window(sR2);
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             double b5 = (double)__fmul_rn(w[o + N], a.g[0]);
@@ -756,9 +781,7 @@ __device__ __forceinline__ void pe_tile_fast(const PolyArgs& a, unsigned char* p
             for (int k = 1; k <= N; k++) b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(w[o + N + k], w[o + N - k]), a.g[k]));
             o2[o] = (float)__dadd_rn(c1[o], __dmul_rn(b5, a.ig33));
         }
-        q = reinterpret_cast<const double2*>(sR1 + ly * RP + lx0);
-#pragma unroll
-        for (int j = 0; j < (4 + 2 * N) / 2; j++) { const double2 t = q[j]; w[2 * j] = (float)t.x; w[2 * j + 1] = (float)t.y; }
+        load_window(sR1);
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             double b3 = (double)__fmul_rn(w[o + N], a.g[0]), b6 = 0;

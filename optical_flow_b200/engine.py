@@ -146,6 +146,23 @@ class Farneback:
     def set_option(self, name, value):
         self._check(self._L.ofb_set_option(self._h, name.encode(), int(value)))
 
+    def shot_chunk(self, W, H, n_pairs):
+        """Pairs per launch the shot / pairs entry points use for this geometry (option "batch" or the engine's default)."""
+        return self._L.ofb_shot_chunk(self._h, int(W), int(H), int(n_pairs))
+
+    def chunk_starts(self, W, H, n_pairs):
+        """First pair of every chunk of a shot of n_pairs pairs: B/4, B/2, B, ..., B, B/2, B/4 (engine.cu host_impl)."""
+        B = self.shot_chunk(W, H, n_pairs)
+        head, tail = ([B // 4, B // 2], [B // 2, B // 4]) if (n_pairs >= 4 * B and B >= 8) else ([], [])
+        starts, t = [], 0
+        for v in head:
+            starts.append(t); t += v
+        while n_pairs - sum(tail) - t > 0:
+            starts.append(t); t += min(B, n_pairs - sum(tail) - t)
+        for v in tail:
+            starts.append(t); t += v
+        return starts
+
     def check_guards(self):
         """Number of overwritten guard bytes around the current workspaces (0 = no out-of-bounds write next to a buffer)."""
         n = self._L.ofb_debug_check_guards(self._h)

@@ -77,13 +77,17 @@ def shot_1080p():
 
 
 def test_1080p_300_pair_shot_at_default_batch_matches_cv2_at_every_seam(eng, cv2, shot_1080p):
-    """configs[1] exactly as bench.py runs it: 301 frames, default batch (24), host API and device-resident API.
-    Chunks start at pairs 0 | 6 | 18 | 42 | ... | 258 | 282 | 294; the 48-slot frame ring wraps at frames 48, 96, ...
+    """configs[1] exactly as bench.py runs it: 301 frames, default chunk (48 pairs per launch), host API and device-resident
+    API.  Chunks start at pairs 0 | 12 | 36 | 84 | ... | 228 | 264 | 288; the 2B+1-slot frame ring wraps near frame 96.
     Compared with cv2: both sides of every kind of seam, the ring wrap, the middle and the last pair."""
     frames = shot_1080p
     P, H, W = frames.shape[0] - 1, frames.shape[1], frames.shape[2]
     n = W * H
-    pairs = [0, 5, 6, 17, 18, 41, 42, 47, 48, 150, 281, 282, 293, 294, 299]
+    B = eng.shot_chunk(W, H, P)
+    starts = eng.chunk_starts(W, H, P)
+    assert starts[0] == 0 and len(starts) >= 5 and starts[1] == B // 4 and P - starts[-1] == B // 4, starts
+    seams = starts[1:4] + starts[-2:]
+    pairs = sorted(set([0, 2 * B - 1, 2 * B, 2 * B + 1, P // 2, P - 1] + [s - 1 for s in seams] + seams))
     # device-resident entry point (bench.py's device leg): all pictures and all flows stay in HBM
     d_frames = eng.device_alloc(frames.nbytes)
     d_bgr = eng.device_alloc(P * n * 3)
@@ -95,14 +99,14 @@ def test_1080p_300_pair_shot_at_default_batch_matches_cv2_at_every_seam(eng, cv2
         for t in pairs:
             flows[t] = np.empty((H, W, 2), np.float32); eng.d2h(flows[t], d_flow + t * n * 8)
             pics[t] = np.empty((H, W, 3), np.uint8); eng.d2h(pics[t], d_bgr + t * n * 3)
-        _check_pairs(cv2, frames, flows, pics, pairs, REF, "1080p shot_device batch 24")
+        _check_pairs(cv2, frames, flows, pics, pairs, REF, "1080p shot_device chunk %d" % B)
         # host entry point (bench.py's e2e leg): every picture equals the device-resident one, bit for bit
         host = eng.shot(frames, want_bgr=True, **REF)["bgr"]
         all_dev = np.empty((P, H, W, 3), np.uint8)
         eng.d2h(all_dev, d_bgr)
         assert np.array_equal(host, all_dev), "ofb_shot_host and ofb_shot_device disagree"
         # and the single-pair drop-in call gives the same flow as the batched ring-slot path
-        for t in (0, 47, 48, 299):
+        for t in (0, pairs[3], pairs[4], P - 1):
             one = eng.calc(frames[t], frames[t + 1], None, **REF)
             assert np.array_equal(one, flows[t]), t
     finally:
@@ -126,12 +130,17 @@ def test_1080p_two_rank_shard_seam_matches_cv2_and_the_unsharded_shot(eng, cv2, 
 
 
 def test_4k_gaussian_shot_matches_cv2(eng, cv2):
-    """configs[2] through the batched shot path (default batch 6 at 4K): 3840x2160, levels 5, poly_n 7, sigma 1.5,
-    OPTFLOW_FARNEBACK_GAUSSIAN; chunk seam at pair 6, last chunk of one pair."""
+    """configs[2] through the batched shot path: 3840x2160, levels 5, poly_n 7, sigma 1.5, OPTFLOW_FARNEBACK_GAUSSIAN, chunks of
+    6 pairs (the 4K default is 12; 6 puts a chunk seam at pair 6 and a last chunk of one pair inside a 13-pair shot)."""
     import synth_frames
     kw = dict(pyr_scale=0.5, levels=5, winsize=15, iterations=3, poly_n=7, poly_sigma=1.5, flags=256)
     frames = synth_frames.shot(3840, 2160, 14, seed=7)
-    res = eng.shot(frames, want_bgr=True, want_flow=True, **kw)
+    assert eng.shot_chunk(3840, 2160, 100) == 12
+    eng.set_option("batch", 6)
+    try:
+        res = eng.shot(frames, want_bgr=True, want_flow=True, **kw)
+    finally:
+        eng.set_option("batch", 0)
     _check_pairs(cv2, frames, res["flow"], res["bgr"], [0, 5, 6, 12], kw, "4K gaussian shot")
 
 

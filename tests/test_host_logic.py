@@ -19,7 +19,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     L = _lib.load()
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.ofb_abi_version() == 3
+    assert L.ofb_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_a_device():
