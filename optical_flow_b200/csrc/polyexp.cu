@@ -237,9 +237,15 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
                 r2 = r2 + a.xxg[k] * p;
             }
             const int ty = VS * g + o;
-            sR0[ty * RP + px] = (double)r0;
-            sR1[ty * RP + px] = (double)r1;
-            sR2[ty * RP + px] = (double)r2;
+            if (exact) {            // cv2's row buffers are f32: kept as f32 in the same arrays (same index), see pe_tile_fast
+                reinterpret_cast<float*>(sR0)[ty * RP + px] = r0;
+                reinterpret_cast<float*>(sR1)[ty * RP + px] = r1;
+                reinterpret_cast<float*>(sR2)[ty * RP + px] = r2;
+            } else {
+                sR0[ty * RP + px] = (double)r0;
+                sR1[ty * RP + px] = (double)r1;
+                sR2[ty * RP + px] = (double)r2;
+            }
         }
     };
     bool vertical_done = false;                          // block-uniform
@@ -407,9 +413,15 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
                 r1 = r1 + a.xg[k] * (hi - lo);
                 r2 = r2 + a.xxg[k] * p;
             }
-            sR0[ty * RP + px] = (double)r0;
-            sR1[ty * RP + px] = (double)r1;
-            sR2[ty * RP + px] = (double)r2;
+            if (exact) {
+                reinterpret_cast<float*>(sR0)[ty * RP + px] = r0;
+                reinterpret_cast<float*>(sR1)[ty * RP + px] = r1;
+                reinterpret_cast<float*>(sR2)[ty * RP + px] = r2;
+            } else {
+                sR0[ty * RP + px] = (double)r0;
+                sR1[ty * RP + px] = (double)r1;
+                sR2[ty * RP + px] = (double)r2;
+            }
         }
     }
     __syncthreads();
@@ -429,11 +441,11 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
     if (exact) {
         // cv2's own float / double mix (FarnebackPolyExp; oracle/farneback_oracle.c orc_polyexp; k_polyexp_tiled): the sums and
         // differences of the f32 rows are formed in FLOAT, four of the six products too, every accumulation is a separate
-        // double multiply and add.  The shared arrays hold the f32 vertical results widened exactly, so (float) gives them back.
+        // double multiply and add.  The shared arrays hold the f32 vertical results as f32 in this mode.
         float w[4 + 2 * N];
-        const double* q = sR0 + ly * RP + lx0;
+        const float* q = reinterpret_cast<const float*>(sR0) + ly * RP + lx0;
 #pragma unroll
-        for (int j = 0; j < 4 + 2 * N; j++) w[j] = (float)q[j];
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             double b1 = (double)__fmul_rn(w[o + N], a.g[0]), b2 = 0, b4 = 0;
@@ -448,9 +460,9 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
             o1[o] = (float)__dmul_rn(b2, a.ig11);
             o3[o] = (float)__dadd_rn(c1[o], __dmul_rn(b4, a.ig33));
         }
-        q = sR2 + ly * RP + lx0;
+        q = reinterpret_cast<const float*>(sR2) + ly * RP + lx0;
 #pragma unroll
-        for (int j = 0; j < 4 + 2 * N; j++) w[j] = (float)q[j];
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             double b5 = (double)__fmul_rn(w[o + N], a.g[0]);
@@ -458,9 +470,9 @@ __device__ __forceinline__ void pe_tile(const PolyArgs& a, unsigned char* pe_sme
             for (int k = 1; k <= N; k++) b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(w[o + N + k], w[o + N - k]), a.g[k]));
             o2[o] = (float)__dadd_rn(c1[o], __dmul_rn(b5, a.ig33));
         }
-        q = sR1 + ly * RP + lx0;
+        q = reinterpret_cast<const float*>(sR1) + ly * RP + lx0;
 #pragma unroll
-        for (int j = 0; j < 4 + 2 * N; j++) w[j] = (float)q[j];
+        for (int j = 0; j < 4 + 2 * N; j++) w[j] = q[j];
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             double b3 = (double)__fmul_rn(w[o + N], a.g[0]), b6 = 0;
