@@ -186,3 +186,15 @@ def test_error_is_a_cv2_error_and_argument_errors_need_no_gpu():
         validate_call(np.zeros((8, 8), np.uint8), np.zeros((8, 9), np.uint8), None, 0.5, 0)
     with pytest.raises(cv2.error):
         validate_call(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.uint8), None, 1.0, 0)
+
+
+def test_update_matrices_kernels_hold_no_contracted_packed_fma():
+    """The UpdateMatrices kernels use packed f32x2 multiplies; ptxas contracts a packed multiply feeding a packed add into FFMA2
+    even under .rn / -fmad=false, which would round once where cv2 rounds twice (csrc/um_device.cuh).  The built library's SASS
+    must hold no FFMA2 in k_um0 / k_iter / k_iter64 / k_update_matrices (tools/check_sass.sh; needs cuobjdump, no GPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    r = subprocess.run([os.path.join(ROOT, "tools", "check_sass.sh")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
