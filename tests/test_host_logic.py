@@ -198,3 +198,27 @@ def test_update_matrices_kernels_hold_no_contracted_packed_fma():
         pytest.skip("cuobjdump not on PATH")
     r = subprocess.run([os.path.join(ROOT, "tools", "check_sass.sh")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_chunk_starts_mirror_the_engine_schedule():
+    """Farneback.chunk_starts restates engine.cu's chunk schedule (B/4, B/2, B, ..., B, B/2, B/4 for a long job, plain chunks for a
+    short one) from the chunk size the library reports; here with the library call replaced by the documented rule."""
+    eng = ofb.Farneback.__new__(ofb.Farneback)          # no context: only the pure-Python schedule is exercised
+
+    def rule(W, H, n_pairs):                             # ofb_shot_chunk's documented default
+        b = -(-96_000_000 // (W * H))
+        b = max(4, min((b + 3) // 4 * 4, 512))
+        if n_pairs < 4 * b:
+            q = ((n_pairs + 3) // 4 + 3) // 4 * 4
+            b = max(max(4, b // 4), min(q, b))
+        return max(1, min(b, n_pairs))
+
+    eng.shot_chunk = rule
+    assert rule(1920, 1080, 300) == 48 and rule(3840, 2160, 100) == 12 and rule(129, 72, 4096) == 512
+    assert eng.chunk_starts(1920, 1080, 300) == [0, 12, 36, 84, 132, 180, 228, 264, 288]
+    assert rule(1920, 1080, 38) == 12 and eng.chunk_starts(1920, 1080, 38) == [0, 12, 24, 36]      # one rank of an 8-way sharded shot
+    assert rule(1920, 1080, 1) == 1 and eng.chunk_starts(1920, 1080, 1) == [0]
+    for n in (1, 5, 47, 48, 191, 192, 193, 300, 1000):
+        st = eng.chunk_starts(1920, 1080, n)
+        assert st[0] == 0 and st == sorted(set(st)) and st[-1] < n
+        assert max(b - a for a, b in zip(st, st[1:] + [n])) <= rule(1920, 1080, n)
