@@ -10,7 +10,7 @@
 //   * a packed ADD (FADD2) is used only where neither operand is a product: ptxas contracts mul.rn.f32x2 feeding
 //     add.rn.f32x2 into FFMA2 even under .rn and -fmad=false (seen in SASS), which would round once instead of twice.
 //     A scalar FADD fed by a packed product is left alone (also checked in SASS: tools/check_sass.sh greps for FFMA2).
-// 54 floating-point instructions per interior pixel instead of 77; results bit-identical (stage tests against the C oracle).
+// 51 floating-point instructions per interior pixel instead of 77; results bit-identical (stage tests against the C oracle).
 #pragma once
 #include "common.cuh"
 
