@@ -35,8 +35,9 @@ namespace ofb {
 // ------------------------------------------------------------------------------------------------
 // k_um0
 // ------------------------------------------------------------------------------------------------
-// CTA = UM0_BX x UM0_BY pixels, one pixel per thread.  Measured on B200 (1080p, ms per 300-pair step): 32x8 9.1, 32x16 9.6,
-// 64x4 9.0, 32x4 8.6, 128x1 8.7, 64x1 8.7, 256x1 9.2, 64x2 8.5 -- small CTAs of two long rows hide the gathers best.
+// CTA = UM0_BX x UM0_BY threads, UM0_ROWS consecutive rows per thread.  Block shape measured on B200 with one row per thread (1080p,
+// ms per 300-pair step): 32x8 9.1, 32x16 9.6, 64x4 9.0, 32x4 8.6, 128x1 8.7, 64x1 8.7, 256x1 9.2, 64x2 8.5 -- small CTAs of two long
+// rows hide the gathers best; rows per thread: 1 / 2 / 4 / 8 -> 8.74 / 8.62 / 7.93 / 7.81 (profiles/r2x_ab_um_packed_rows.log).
 #ifndef OFB_UM0_BX
 #define OFB_UM0_BX 64
 #endif
@@ -69,7 +70,7 @@ k_um0(Um0Args a)
     const float2* const fl = reinterpret_cast<const float2*>(      // SRC 1: this scale's flow; SRC 2: the coarser one
         __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(a.flow + (size_t)z * a.flow_item), 0));
     __builtin_assume(__isGlobal(mout));
-    __builtin_assume(__isGlobal(fl));
+    if (SRC != 0) __builtin_assume(__isGlobal(fl));            // SRC 0 has no flow (a.flow may be null) and never touches fl
     if (x >= a.W || ybeg >= a.H) return;
     const int yend = min(ybeg + UM0_ROWS, a.H);
     const UmBase ub = um_base(a.R, a.slot0, z);                 // M and R of a level share pitch and plane size (launch_um0)
@@ -92,11 +93,11 @@ k_um0(Um0Args a)
         } else if (SRC == 2) {
             const int sy = a.uy[y];
             const float b1 = a.uay[y], b0 = 1.f - b1;
-            const unsigned o0 = (unsigned)sy * (unsigned)a.Wp;                  // one item of the coarse flow is far below 2^32 pixels
-            const unsigned o1 = (unsigned)min(sy + 1, a.Hp - 1) * (unsigned)a.Wp;
+            const unsigned c0 = (unsigned)sy * (unsigned)a.Wp;                  // one item of the coarse flow is far below 2^32 pixels
+            const unsigned c1 = (unsigned)min(sy + 1, a.Hp - 1) * (unsigned)a.Wp;
             // hx = p0.x*a0 + p1.x*a1 per row, d = (h0*b0 + h1*b1) * mul: products packed over (x, y), adds scalar (um_device.cuh)
-            const float2 t00 = mul2s(fl[o0 + sx], a0), t01 = mul2s(fl[o0 + sx1], a1);
-            const float2 t10 = mul2s(fl[o1 + sx], a0), t11 = mul2s(fl[o1 + sx1], a1);
+            const float2 t00 = mul2s(fl[c0 + sx], a0), t01 = mul2s(fl[c0 + sx1], a1);
+            const float2 t10 = mul2s(fl[c1 + sx], a0), t11 = mul2s(fl[c1 + sx1], a1);
             const float2 h0 = mul2s(make_float2(t00.x + t01.x, t00.y + t01.y), b0);
             const float2 h1 = mul2s(make_float2(t10.x + t11.x, t10.y + t11.y), b1);
             const float2 d = mul2s(make_float2(h0.x + h1.x, h0.y + h1.y), a.mul);
