@@ -2,7 +2,7 @@
 endpoint difference to cv2 exceeds 1e-2 px, what do cv2 / the oracle / the single-pair call give there."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import cv2
 import optical_flow_b200 as ofb
 import synth_frames

@@ -2,12 +2,12 @@
 GPU vs cv2 on the 1080p stress input for several engine-option sets."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import cv2
 import optical_flow_b200 as ofb
 import importlib.util
-spec = importlib.util.spec_from_file_location("tb", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "test_gpu_benchpath.py"))
+spec = importlib.util.spec_from_file_location("tb", os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "test_gpu_benchpath.py"))
 tb = importlib.util.module_from_spec(spec); spec.loader.exec_module(tb)
 from oracle import c_oracle
 c_oracle.build()

@@ -1,7 +1,7 @@
 """Which part of exact_arithmetic matters on flat regions with sensor noise (tests/test_gpu_benchpath.py's scene)?"""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import cv2
 import optical_flow_b200 as ofb

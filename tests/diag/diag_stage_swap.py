@@ -2,7 +2,7 @@
 Tells which stage's (tolerated) per-stage difference is amplified into the end-to-end deviation on rank-deficient input."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cv2
 import optical_flow_b200 as ofb

@@ -39,6 +39,12 @@ def test_product_never_imports_the_oracle_or_cv2_compute():
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "liboracle" not in src, f
                 assert "cv2.calcOpticalFlowFarneback(" not in src.replace("cv2.calcOpticalFlowFarneback(prev", ""), f
+    # the entry-point scripts and the tools are not allowed to reach the oracle either: only tests/ (diagnostics included),
+    # __graft_entry__.smoke() and bench.py (cpu_baseline / reference arm / the post-timing parity check) do
+    for f in ["optical_flow.py", "visualize_optical_flow.py", "synth_frames.py"] + \
+             [os.path.join("tools", t) for t in os.listdir(os.path.join(ROOT, "tools")) if t.endswith((".py", ".sh"))]:
+        src = open(os.path.join(ROOT, f)).read()
+        assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
 
 
 def test_scale_schedule_matches_oracle(oracle):

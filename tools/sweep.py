@@ -32,8 +32,14 @@ def _cv2_pair(args):
     import cv2
     f = cv2.calcOpticalFlowFarneback(prev, nxt, None, prm["pyr_scale"], prm["levels"], prm["winsize"], prm["iterations"],
                                      prm["poly_n"], prm["poly_sigma"], prm["flags"])
-    from oracle import cv2_reference
-    return int(cv2_reference.viz(f)[0, 0, 0])
+    # the four picture lines of visualize_optical_flow.py:48-55, as bench.py's cpu_baseline leg runs them
+    import numpy as np
+    mag, ang = cv2.cartToPolar(f[..., 0], f[..., 1])
+    hsv = np.zeros(prev.shape + (3,), np.uint8)
+    hsv[..., 1] = 255
+    hsv[..., 0] = ang * 180 / np.pi
+    hsv[..., 2] = cv2.normalize(mag, None, 0, 255, cv2.NORM_MINMAX)
+    return int(cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)[0, 0, 0])
 
 
 def main():
